@@ -1,0 +1,154 @@
+"""CPU: the NumPy oracle against the committed golden fixtures (outputs of the unmodified
+reference, tests/golden/make_golden.py) -- pins the oracle without needing /root/reference."""
+import numpy as np
+import pytest
+
+from oracle import dmrg_oracle as orc
+
+CASES = ["a", "b", "c", "d"]
+TOL = 1e-13  # pure sums of products
+
+
+def rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+@pytest.mark.parametrize("mode", ["blas", "einsum"])
+@pytest.mark.parametrize("c", CASES)
+def test_heff_onesite(golden, c, mode):
+    g = golden["kernels"]
+    x = g[c + "_x1"]
+    y = orc.heff_onesite(x.ravel(), [g[c + "_L"]], [g[c + "_W1"]], [g[c + "_R"]], x.shape, mode)
+    assert rel(y, g[c + "_y1"]) < TOL
+
+
+@pytest.mark.parametrize("mode", ["blas", "einsum"])
+@pytest.mark.parametrize("c", CASES)
+def test_heff_twosite(golden, c, mode):
+    g = golden["kernels"]
+    x = g[c + "_x2"]
+    y = orc.heff_twosite(x.ravel(), [g[c + "_L"]], [g[c + "_W1"]], [g[c + "_W2"]], [g[c + "_R"]], x.shape, mode)
+    assert rel(y, g[c + "_y2"]) < TOL
+
+
+@pytest.mark.parametrize("mode", ["blas", "einsum"])
+@pytest.mark.parametrize("c", CASES)
+def test_env_updates(golden, c, mode):
+    g = golden["kernels"]
+    A, W, L, R = g[c + "_A"], g[c + "_W1"], g[c + "_L"], g[c + "_R"]
+    assert rel(orc.env_update_right(A, W, L, None, mode), g[c + "_envR_out"]) < TOL
+    assert rel(orc.env_update_left(A, W, R, None, mode), g[c + "_envL_out"]) < TOL
+    assert rel(orc.env_update_right(A, W, L, g[c + "_Abra"], mode), g[c + "_envR_bra_out"]) < TOL
+    assert rel(orc.env_update_left(A, None, R, g[c + "_Abra"], mode), g[c + "_envL_none_out"]) < TOL
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_dense_matches_matvec(golden, c):
+    g = golden["kernels"]
+    x = g[c + "_x1"]
+    H = orc.heff_dense_onesite([g[c + "_L"]], [g[c + "_W1"]], [g[c + "_R"]], x.shape)
+    assert rel(-H @ x.ravel(), g[c + "_y1"]) < TOL
+    x2 = g[c + "_x2"]
+    H2 = orc.heff_dense_twosite([g[c + "_L"]], [g[c + "_W1"]], [g[c + "_W2"]], [g[c + "_R"]], x2.shape)
+    assert rel(-H2 @ x2.ravel(), g[c + "_y2"]) < TOL
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_svd_truncate(golden, c):
+    g = golden["kernels"]
+    x2 = g[c + "_x2"]
+    mbd = int(g[c + "_svd_mbd"])
+    A, B, S, EE, EEs = orc.svd_truncate_twosite(x2.ravel(), x2.shape, mbd)
+    assert np.allclose(S, g[c + "_svd_S"], rtol=1e-12, atol=0)
+    assert abs(EE - g[c + "_svd_EE"]) < 1e-12
+    assert np.allclose(EEs, g[c + "_svd_EEs"], rtol=1e-10, atol=1e-14)
+    # tensors only up to gauge: compare projectors
+    Ar, Br = g[c + "_svd_A"], g[c + "_svd_B"]
+    assert A.shape == Ar.shape and B.shape == Br.shape
+    d, Dl, k = A.shape
+    Pa = lambda T: (lambda m: m @ m.conj().T)(T.swapaxes(0, 1).reshape(Dl * d, k))
+    assert rel(Pa(A), Pa(Ar)) < 1e-10
+
+
+def test_davidson_restatement(golden):
+    g = golden["davidson"]
+    L, R, W, x0 = g["L"], g["R"], g["W"], g["x0"]
+    stats = {}
+    mv = lambda x: orc.heff_onesite(x, [L], [W], [R], x0.shape)
+    e, xs = orc.davidson_nosym(mv, [x0.ravel()], nroots=1, stats=stats)
+    # same algorithm, same arithmetic order up to BLAS vs einsum rounding
+    assert abs(e[0] - g["eval"]) < 1e-9 * abs(g["eval"])
+    assert abs(stats["n_matvec"] - int(g["n_matvec"])) <= max(3, int(0.05 * int(g["n_matvec"])))
+    # eigenvector up to phase
+    v, vr = xs[0], g["evec"]
+    assert abs(abs(np.vdot(v, vr)) / (np.linalg.norm(v) * np.linalg.norm(vr)) - 1) < 1e-10
+    # Ritz value vs dense eigenvalue: the reference's own floor (residual <= 1e-7)
+    assert abs(e[0] - g["exact_min_real"]) < 1e-6
+
+
+def test_config0_tasep(golden):
+    """BASELINE.json configs[0]: TASEP N=10 chi=10 s=-0.5, one-site finite DMRG."""
+    from oracle.dmrg_oracle import run_dmrg_onesite
+    g = golden["runs"]
+    mpo = _asep_mpo(10, g["cfg0_params"])
+    np.random.seed(0)
+    E, EE, EEs, _, _ = run_dmrg_onesite(mpo, 10, tol=1e-8, max_iter=10)
+    assert abs(E - g["cfg0_davidson_E"]) < 1e-8 * abs(g["cfg0_davidson_E"])
+    assert abs(E - g["cfg0_exact_E"]) < 2e-7
+    np.random.seed(0)
+    E2, EE2, _, _, _ = run_dmrg_onesite(mpo, 10, tol=1e-8, max_iter=10, alg="exact")
+    assert abs(E2 - g["cfg0_exact_E"]) < 1e-10 * abs(g["cfg0_exact_E"])
+
+
+def test_small_runs_vs_ed(golden):
+    g = golden["runs"]
+    for tag in ("tasep6", "asep6"):
+        mpo = _asep_mpo(6, g[tag + "_params"])
+        np.random.seed(3)
+        E, EE, EEs, mps, _ = orc.run_dmrg_onesite(mpo, 8, tol=1e-10, max_iter=6)
+        assert abs(E - g[tag + "_dmrg_E"]) < 2e-8
+        assert abs(E - g[tag + "_ed_top"]) < 5e-8
+        assert abs(EE - g[tag + "_dmrg_EE"]) < 1e-6
+        # two-site finite sweep (composition) has the same fixed point
+        np.random.seed(3)
+        E2 = orc.run_dmrg_twosite(mpo, 8, n_sweeps=3)[0]
+        assert abs(E2 - g[tag + "_ed_top"]) < 5e-8
+
+
+def test_full_contract(golden):
+    g = golden["runs"]
+    for tag in ("tasep6", "asep6"):
+        mps = [g[tag + "_mps%d" % i] for i in range(6)]
+        mpo = _asep_mpo(6, g[tag + "_params"])
+        den = orc.full_contract(None, mps)
+        e = orc.full_contract(mpo, mps) / den
+        assert abs(e - g[tag + "_energy_rr"]) < 1e-12
+        cur = orc.full_contract(_asep_curr_mpo(6, g[tag + "_params"]), mps) / den
+        assert abs(cur - g[tag + "_current_rr"]) < 1e-12
+
+
+def test_idmrg(golden):
+    g = golden["runs"]
+    mpo4 = _asep_mpo(4, (0.2, 0.8, 0.1, 0.9, 0.4, 0.6, -0.5))
+    np.random.seed(5)
+    E, EE, EEs, S, N, _, _ = orc.run_idmrg(mpo4, 10, max_iter=20)
+    assert abs(E - g["idmrg_E"]) < 1e-6 * abs(g["idmrg_E"])
+    assert abs(EE - g["idmrg_EE"]) < 1e-6
+
+
+def test_heisenberg_mpo_two_sites():
+    mpo = orc.heisenberg_mpo(2, sign=1.0)
+    H = np.einsum("abij,bckl->ikjl", mpo[0][0], mpo[0][1]).reshape(4, 4)
+    ev = np.sort(np.linalg.eigvalsh(H))
+    assert np.allclose(ev, [-0.75, 0.25, 0.25, 0.25])
+
+
+# ---- model builders shared by tests (data only) ---------------------------------------
+def _asep_mpo(N, prm):
+    from pydmrg_b200.mpo import asep_mpo
+    return asep_mpo(N, tuple(float(v) for v in prm))
+
+
+def _asep_curr_mpo(N, prm):
+    from pydmrg_b200.mpo import asep_curr_mpo
+    return asep_curr_mpo(N, tuple(float(v) for v in prm))
