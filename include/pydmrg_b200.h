@@ -1,0 +1,149 @@
+/*
+ * pydmrg_b200 -- C ABI of the B200-native (sm_100a) DMRG sweep hot path.
+ *
+ * The reference (philliphelms/PyDMRG) is pure Python and has no FFI of its own; its seam
+ * for this path is the closure / step-function contract
+ *     Hfun(x) -> -H_eff x                          pydmrg/tools/diag_tools.py:108-125, 146-162
+ *     update_envR / update_envL                    pydmrg/tools/env_tools.py:40-50, 28-38
+ *     davidson(aop, x0, precond, ...)              pydmrg/tools/la_tools.py:315-557
+ *     renorm_inf (two-site SVD truncation)         pydmrg/tools/mps_tools.py:98-120
+ *     renormalizeR / renormalizeL (RDM route)      pydmrg/dmrg.py:49-136
+ * Each entry point below names the reference lines it replaces.  The reference-side binding
+ * is a ctypes stub; pydmrg_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are C-order (row-major) exactly as the reference's NumPy arrays;
+ *   - dtype: PDMRG_F64 = float64, PDMRG_C128 = interleaved complex128 (NumPy layout);
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream`; no call
+ *     synchronises the stream unless stated;
+ *   - return value 0 = success, non-zero = error, message from pdmrg_last_error();
+ *   - no hidden device allocation: scratch space is passed in by the caller (sizes from the
+ *     *_workspace_bytes queries); plan objects own only a few KB of MPO coefficients.
+ */
+#ifndef PYDMRG_B200_H
+#define PYDMRG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDMRG_F64 0
+#define PDMRG_C128 1
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* pdmrg_last_error(void);
+int pdmrg_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long pdmrg_launch_count(void);
+/* which GEMM path the last pdmrg_gemm_nt call took: 1 = DMMA+TMA tiles, 2 = generic */
+int pdmrg_last_gemm_path(void);
+/* force the generic (non-TMA) GEMM kernel; testing only */
+void pdmrg_set_force_generic_gemm(int on);
+
+/* ---- dense building block -------------------------------------------------------------
+ * C[b] (M x N, ldc) = alpha * A[b] (M x K, lda) * op(B[b] (N x K, ldb))^T + beta * C[b]
+ * op = conj when conjB != 0 (complex only).  Leading dimensions and batch strides are in
+ * ELEMENTS of the dtype.  strideA / strideB = 0 broadcasts that operand over the batch.
+ * beta must be 0 or 1.  This is the tile engine under every contraction of
+ * tools/diag_tools.py:114-119,153-156 and tools/env_tools.py:35-37,47-49. */
+int pdmrg_gemm_nt(int dtype, int M, int N, int K, int batch,
+                  const void* A, long long lda, long long strideA,
+                  const void* B, long long ldb, long long strideB, int conjB,
+                  void* C, long long ldc, long long strideC,
+                  double alpha_re, double alpha_im, int beta, void* stream);
+
+/* ---- strided 4-index copy:  out[i0,i1,i2,i3] (C-order, dims n0..n3) = f(in[sum i_k*s_k])
+ * f = conj if conj != 0; if scale != NULL the element is multiplied by the REAL vector
+ * scale[i_{scale_axis}] (device pointer).  Strides in elements. */
+int pdmrg_permute4(int dtype, const void* in, void* out,
+                   int n0, int n1, int n2, int n3,
+                   long long s0, long long s1, long long s2, long long s3,
+                   int conj, const double* scale, int scale_axis, void* stream);
+
+/* ---- effective-Hamiltonian mat-vec  (H1: tools/diag_tools.py:108-125,
+ *                                       H2: tools/diag_tools.py:146-162) -------------------
+ * One plan per local problem.  P = physical dimension of the local block (d for one-site,
+ * d1*d2 for two-site).  For each MPO term m the caller passes the COMBINED local operator
+ *   Wc[m] : dense (wL*P) x (wR*P) C-order, Wc[(j,pout),(o,pin)]
+ *           one-site: Wc[(n,o),(j,l)] = W[n,j,o,l];
+ *           two-site: Wc[(j,(m,p)),(o,(n,q))] = sum_l W1[j,l,m,n] W2[l,o,p,q]
+ * (host pointer, dtype of the plan).  Zero entries are skipped (MPO block sparsity).
+ * y[pout,i,r] = sign * sum_m sum L_m[i,j,k] Wc_m[(j,pout),(o,pin)] R_m[r,o,s] x[pin,k,s]
+ * with L_m (Dl,wL,Dl), R_m (Dr,wR,Dr), x and y (P,Dl,Dr).  The reference's Hfun returns
+ * -H x, i.e. sign = -1. */
+typedef struct pdmrg_heff_plan pdmrg_heff_plan;
+int pdmrg_heff_plan_create(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                           const int* wL_host, const int* wR_host, const void* const* Wc_host);
+void pdmrg_heff_plan_destroy(pdmrg_heff_plan* plan);
+size_t pdmrg_heff_workspace_bytes(const pdmrg_heff_plan* plan);
+int pdmrg_heff_apply(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs,
+                     const void* x, void* y, double sign, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* MPO-bond-sharded variant: this rank applies only the (j,o) blocks whose
+ * flag in block_mask_host[m][j*wR+o] is non-zero; y holds the PARTIAL sum (caller
+ * all-reduces).  The mask is fixed at plan creation. */
+int pdmrg_heff_plan_create_sharded(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                   const int* wL_host, const int* wR_host, const void* const* Wc_host,
+                                   const unsigned char* const* block_mask_host);
+/* algorithmic FLOPs of one apply (dense-W count of SURVEY 8d) and with block sparsity */
+double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan);
+double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan);
+
+/* ---- environment (block) updates  (E1: tools/env_tools.py:40-50, E2: :28-38) --------------
+ * right-growing:  out[k,m,q] = sum L[j,l,p] Abra[i,j,k] W[l,m,i,n] A[n,p,q]
+ *   A, Abra (d,Dl,Dr); L (Dl,wl,Dl); W host (wl,wr,d,d) dtype-typed or NULL (= identity,
+ *   wr = wl); out (Dr,wr,Dr).  Abra = NULL means conj(A) (env_tools.py:41).
+ * left-growing:   out[x,y,a] = sum B[e,a,f] R[c,d,f] W[y,d,b,e] Bbra[b,x,c]
+ *   B, Bbra (d,Dl,Dr); R (Dr,wr,Dr); out (Dl,wl,Dl). */
+size_t pdmrg_env_workspace_bytes(int dtype, int d, int Dl, int Dr, int wl, int wr);
+int pdmrg_env_update_right(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                           const void* L, const void* A, const void* Abra, void* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int pdmrg_env_update_left(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                          const void* R, const void* B, const void* Bbra, void* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Krylov vector kernels for the Davidson loop (tools/la_tools.py:449-457, 469-470,
+ *      479-482, 524-536).  Vectors have n elements; a "basis" is m vectors at X + i*stride. */
+/* out_dev[i] = <X_i | y> = sum conj(X_i) y, i < m   (out_dev: m elements of dtype) */
+int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long long stride,
+                   const void* y, void* out_dev, void* scratch, size_t scratch_bytes, void* stream);
+/* out = sum_i coef[i] X_i  (+ out if accumulate);  coef_host: m elements of dtype */
+int pdmrg_vec_combine(int dtype, long long n, int m, const void* coef_host, const void* X,
+                      long long stride, void* out, int accumulate, void* stream);
+/* r = sum_i v[i] (AX_i - e XS_i);  norm2_dev[0] = ||r||^2 (double).  v_host, e_host of dtype */
+int pdmrg_davidson_residual(int dtype, long long n, int m, const void* v_host, const void* e_host,
+                            const void* XS, const void* AX, long long stride, void* r,
+                            double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream);
+/* r = (r * scale_dev[0]^-1/2 if scale_dev) - sum_i c_dev[i] X_i ; norm2_dev[0] = ||r||^2.
+ * Coefficients stay on the device so that dots -> project needs no host round trip. */
+int pdmrg_vec_project(int dtype, long long n, int m, const void* X, long long stride,
+                      const void* c_dev, const double* scale_dev, void* r,
+                      double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream);
+/* out = in * (norm2_dev[0])^-1/2  (out may alias in) */
+int pdmrg_vec_normalize(int dtype, long long n, const void* in, const double* norm2_dev,
+                        void* out, void* stream);
+size_t pdmrg_vec_scratch_bytes(int m);
+
+/* ---- truncation ---------------------------------------------------------------------------
+ * T2 (tools/mps_tools.py:98-120): thin SVD of a row-major (rows x cols) matrix a:
+ *   a = U diag(S) Vh,  U (rows x k) row-major, S (k) descending, Vh (k x cols) row-major,
+ *   k = min(rows, cols).  `a` is destroyed.  method: 0 = QR-iteration (gesvd), 1 = Jacobi
+ *   (gesvdj).  info_dev: one int (device).  cuSOLVER is loaded on first use. */
+size_t pdmrg_svd_workspace_bytes(int dtype, int rows, int cols, int method);
+int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* Vh,
+              int method, void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
+/* T1 (dmrg.py:64-76): eigen-decomposition of a Hermitian (n x n) row-major matrix, in place:
+ * on exit row i of `a` is the i-th eigenvector (ascending eigenvalues in w). */
+size_t pdmrg_heevd_workspace_bytes(int dtype, int n);
+int pdmrg_heevd(int dtype, int n, void* a, double* w, void* workspace, size_t workspace_bytes,
+                int* info_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,321 @@
+// Effective-Hamiltonian mat-vec (H1/H2) and environment updates (E1/E2) composed from the
+// DMMA GEMM tiles (gemm_nt.cu) and the sparse W "mix" (tensor_ops.cu).
+//
+// Mat-vec, per MPO term  (reference: pydmrg/tools/diag_tools.py:114-119 one-site,
+// :153-156 two-site; P = d or d1*d2):
+//   stage A   T[(r,o),(pin,k)] = sum_s R[r,o,s] x[pin,k,s]        GEMM  (Dr*wR) x (P*Dl) x Dr
+//   mix       U[pout,r,j,k]    = sum Wc[(j,pout),(o,pin)] T[r,o,pin,k]   point-wise, sparse
+//   stage C   y[pout,i,r]     += sign sum_{j,k} L[i,j,k] U[pout,r,j,k]   GEMM  Dl x Dr x (wL*Dl), batch P
+// Stage A is issued as a GEMM batched over the MPO-bond index o of R (and stage C over
+// contiguous runs of j), so all-zero columns / rows of the local operator -- MPO block
+// sparsity, or the blocks owned by other ranks in the bond-sharded multi-GPU mode --
+// cost no FLOPs.  Every index order is chosen so that both GEMMs are plain "NT" products
+// on the tensors exactly as the reference stores them (no packing of x, L, R or y).
+#include "ops.cuh"
+
+#include <cmath>
+
+using namespace pdmrg;
+
+struct pdmrg_heff_plan {
+  int dtype, P, Dl, Dr, n_mpo;
+  std::vector<int> wL, wR;
+  std::vector<MixOpDev> mix;                         // per MPO term
+  std::vector<std::vector<int>> need_o, need_j;      // per MPO term: flags
+  void* dev_blob = nullptr;
+  double flops_dense = 0, flops_sparse = 0;
+  size_t ws_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+bool is_zero(const T* p) { return p[0] == 0.0; }
+
+int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mpo, const int* wL,
+               const int* wR, const void* const* Wc_host, const unsigned char* const* mask) {
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "heff plan: bad dtype");
+  PDMRG_REQUIRE(P > 0 && Dl > 0 && Dr > 0 && n_mpo > 0, "heff plan: bad extents");
+  auto* pl = new pdmrg_heff_plan();
+  pl->dtype = dtype; pl->P = P; pl->Dl = Dl; pl->Dr = Dr; pl->n_mpo = n_mpo;
+  const int E = dtype == PDMRG_C128 ? 2 : 1;
+  const double cmac = dtype == PDMRG_C128 ? 8.0 : 2.0;
+  std::vector<MixOpHost> hosts(n_mpo);
+  size_t blob_bytes = 0;
+  for (int m = 0; m < n_mpo; ++m) {
+    const int wl = wL[m], wr = wR[m];
+    pl->wL.push_back(wl); pl->wR.push_back(wr);
+    const double* W = static_cast<const double*>(Wc_host[m]);
+    const int rows = wl * P, cols = wr * P;
+    std::vector<int> need_o(wr, 0), need_j(wl, 0);
+    MixOpHost& h = hosts[m];
+    h.rowptr.push_back(0);
+    long long nnz = 0;
+    // rows are ordered (j, pout); input T[r,o,pin,k]; output U[pout,r,j,k]
+    for (int j = 0; j < wl; ++j)
+      for (int po = 0; po < P; ++po) {
+        const int row = j * P + po;
+        for (int o = 0; o < wr; ++o) {
+          if (mask && mask[m] && !mask[m][j * wr + o]) continue;
+          for (int pi = 0; pi < P; ++pi) {
+            const double* w = W + (size_t)E * ((size_t)row * cols + o * P + pi);
+            const bool nz = (w[0] != 0.0) || (E == 2 && w[1] != 0.0);
+            if (!nz) continue;
+            h.in_off.push_back(((long long)o * P + pi) * Dl);
+            h.val.push_back(w[0]);
+            h.val.push_back(E == 2 ? w[1] : 0.0);
+            need_o[o] = 1; need_j[j] = 1;
+            ++nnz;
+          }
+        }
+        h.rowptr.push_back((int)h.in_off.size());
+        h.out_off.push_back((long long)po * Dr * wl * Dl + (long long)j * Dl);
+      }
+    // drop rows of slabs j that are never read by stage C
+    MixOpHost hc;
+    hc.rowptr.push_back(0);
+    for (int j = 0; j < wl; ++j) {
+      if (!need_j[j]) continue;
+      for (int po = 0; po < P; ++po) {
+        const int row = j * P + po;
+        for (int k = h.rowptr[row]; k < h.rowptr[row + 1]; ++k) {
+          hc.in_off.push_back(h.in_off[k]);
+          hc.val.push_back(h.val[2 * k]); hc.val.push_back(h.val[2 * k + 1]);
+        }
+        hc.rowptr.push_back((int)hc.in_off.size());
+        hc.out_off.push_back(h.out_off[row]);
+      }
+    }
+    h = hc;
+    pl->need_o.push_back(need_o); pl->need_j.push_back(need_j);
+    blob_bytes += align_up(h.device_bytes(), 256);
+    int no = 0, nj = 0;
+    for (int v : need_o) no += v;
+    for (int v : need_j) nj += v;
+    const double cube_a = (double)Dr * Dr * Dl, cube_c = (double)Dl * Dl * Dr;
+    pl->flops_dense += cmac * (P * (wr * cube_a + wl * cube_c) + (double)rows * cols * Dl * Dr);
+    pl->flops_sparse += cmac * (P * (no * cube_a + nj * cube_c) + (double)nnz * Dl * Dr);
+    const size_t t_elems = (size_t)Dr * wr * P * Dl, u_elems = (size_t)P * Dr * wl * Dl;
+    const size_t need = align_up(t_elems * 8 * E, 256) + align_up(u_elems * 8 * E, 256);
+    if (need > pl->ws_bytes) pl->ws_bytes = need;
+  }
+  cudaError_t e = cudaMalloc(&pl->dev_blob, blob_bytes ? blob_bytes : 256);
+  if (e != cudaSuccess) { set_error("heff plan: cudaMalloc(%zu) failed: %s", blob_bytes, cudaGetErrorString(e)); delete pl; return 1; }
+  size_t off = 0;
+  for (int m = 0; m < n_mpo; ++m) {
+    MixOpDev dev;
+    if (upload_mix_op(hosts[m], static_cast<unsigned char*>(pl->dev_blob) + off, &dev, 0)) { cudaFree(pl->dev_blob); delete pl; return 1; }
+    pl->mix.push_back(dev);
+    off += align_up(hosts[m].device_bytes(), 256);
+  }
+  e = cudaStreamSynchronize(0);
+  if (e != cudaSuccess) { set_error("heff plan: upload failed: %s", cudaGetErrorString(e)); cudaFree(pl->dev_blob); delete pl; return 1; }
+  *out = pl;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pdmrg_heff_plan_create(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                      const int* wL, const int* wR, const void* const* Wc_host) {
+  return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, nullptr);
+}
+
+extern "C" int pdmrg_heff_plan_create_sharded(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                              const int* wL, const int* wR, const void* const* Wc_host,
+                                              const unsigned char* const* block_mask_host) {
+  return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, block_mask_host);
+}
+
+extern "C" void pdmrg_heff_plan_destroy(pdmrg_heff_plan* plan) {
+  if (!plan) return;
+  if (plan->dev_blob) cudaFree(plan->dev_blob);
+  delete plan;
+}
+
+extern "C" size_t pdmrg_heff_workspace_bytes(const pdmrg_heff_plan* plan) { return plan ? plan->ws_bytes : 0; }
+extern "C" double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan) { return plan ? plan->flops_dense : 0; }
+extern "C" double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan) { return plan ? plan->flops_sparse : 0; }
+
+extern "C" int pdmrg_heff_apply(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x,
+                                void* y, double sign, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(pl != nullptr, "pdmrg_heff_apply: null plan");
+  PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply: workspace too small");
+  const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
+  const int P = pl->P, Dl = pl->Dl, Dr = pl->Dr;
+  bool wrote_y = false;
+  for (int m = 0; m < pl->n_mpo; ++m) {
+    const int wl = pl->wL[m], wr = pl->wR[m];
+    const size_t t_elems = (size_t)Dr * wr * P * Dl;
+    double* T = static_cast<double*>(workspace);
+    double* U = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align_up(t_elems * 8 * E, 256));
+    const double* R = static_cast<const double*>(Rs[m]);
+    const double* L = static_cast<const double*>(Ls[m]);
+    // ---- stage A: batched over runs of needed o
+    bool any = false;
+    for (int o = 0; o < wr;) {
+      if (!pl->need_o[m][o]) { ++o; continue; }
+      int o1 = o;
+      while (o1 < wr && pl->need_o[m][o1]) ++o1;
+      any = true;
+      if (pdmrg_gemm_nt(pl->dtype, Dr, P * Dl, Dr, o1 - o,
+                        R + (size_t)E * o * Dr, (long long)wr * Dr, Dr,
+                        x, Dr, 0, 0,
+                        T + (size_t)E * o * P * Dl, (long long)wr * P * Dl, (long long)P * Dl,
+                        1.0, 0.0, 0, stream))
+        return 1;
+      o = o1;
+    }
+    if (!any) continue;
+    // ---- mix
+    if (launch_mix(pl->dtype, pl->mix[m], T, U, Dr, Dl, (long long)wr * P * Dl, 1, (long long)wl * Dl, 1, stream)) return 1;
+    // ---- stage C: contiguous runs of needed j, accumulated into y
+    for (int j = 0; j < wl;) {
+      if (!pl->need_j[m][j]) { ++j; continue; }
+      int j1 = j;
+      while (j1 < wl && pl->need_j[m][j1]) ++j1;
+      if (pdmrg_gemm_nt(pl->dtype, Dl, Dr, (j1 - j) * Dl, P,
+                        L + (size_t)E * j * Dl, (long long)wl * Dl, 0,
+                        U + (size_t)E * j * Dl, (long long)wl * Dl, (long long)Dr * wl * Dl, 0,
+                        y, Dr, (long long)Dl * Dr, sign, 0.0, wrote_y ? 1 : 0, stream))
+        return 1;
+      wrote_y = true;
+      j = j1;
+    }
+  }
+  if (!wrote_y) PDMRG_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)P * Dl * Dr * 8 * E, stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Environment updates
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct EnvLayout {
+  size_t op_bytes, pack_a, pack_b, t1, v;   // byte sizes (256-aligned)
+  size_t total() const { return op_bytes + pack_a + pack_b + t1 + v; }
+};
+
+EnvLayout env_layout(int dtype, int d, int Dl, int Dr, int wl, int wr) {
+  const size_t eb = elem_bytes(dtype);
+  EnvLayout l;
+  // generous bound for the CSR blob: dense wl*wr*d*d entries
+  const size_t nnz = (size_t)wl * wr * d * d;
+  l.op_bytes = align_up(nnz * (8 + 16) + ((size_t)(wl > wr ? wl : wr) * d + 2) * 16 + 256, 256);
+  l.pack_a = align_up((size_t)d * Dl * Dr * eb, 256);
+  l.pack_b = l.pack_a;
+  const int wmax = wl > wr ? wl : wr;
+  l.t1 = align_up((size_t)d * Dl * Dr * wmax * eb, 256);
+  l.v = l.t1;
+  return l;
+}
+
+// W host tensor (w_a, w_b, d, d) element accessor
+inline const double* w_at(const double* W, int E, int wb, int d, int a, int b, int i, int j) {
+  return W + (size_t)E * ((((size_t)a * wb + b) * d + i) * d + j);
+}
+
+}  // namespace
+
+extern "C" size_t pdmrg_env_workspace_bytes(int dtype, int d, int Dl, int Dr, int wl, int wr) {
+  return env_layout(dtype, d, Dl, Dr, wl, wr).total();
+}
+
+extern "C" int pdmrg_env_update_right(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                                      const void* L, const void* A, const void* Abra, void* out,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "env_update_right: bad dtype");
+  if (!W_host) PDMRG_REQUIRE(wl == wr, "env_update_right: identity MPO entry needs wl == wr");
+  const EnvLayout lay = env_layout(dtype, d, Dl, Dr, wl, wr);
+  PDMRG_REQUIRE(workspace_bytes >= lay.total(), "env_update_right: workspace too small");
+  const int E = dtype == PDMRG_C128 ? 2 : 1;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  void* op_dev = ws;
+  double* At = reinterpret_cast<double*>(ws + lay.op_bytes);
+  double* AbT = reinterpret_cast<double*>(ws + lay.op_bytes + lay.pack_a);
+  double* T1 = reinterpret_cast<double*>(ws + lay.op_bytes + lay.pack_a + lay.pack_b);
+  double* V = reinterpret_cast<double*>(ws + lay.op_bytes + lay.pack_a + lay.pack_b + lay.t1);
+  // At[n,q,p] = A[n,p,q]
+  if (pdmrg_permute4(dtype, A, At, 1, d, Dr, Dl, 0, (long long)Dl * Dr, 1, Dr, 0, nullptr, 0, stream)) return 1;
+  // AbT[k,i,j] = Abra[i,j,k]   (default bra = conj(A), tools/env_tools.py:41)
+  if (pdmrg_permute4(dtype, Abra ? Abra : A, AbT, 1, Dr, d, Dl, 0, 1, (long long)Dl * Dr, Dr, Abra ? 0 : 1, nullptr, 0, stream)) return 1;
+  // T1[(n,q),(j,l)] = sum_p At[(n,q),p] L[(j,l),p]
+  if (pdmrg_gemm_nt(dtype, d * Dr, Dl * wl, Dl, 1, At, Dl, 0, L, Dl, 0, 0, T1, (long long)Dl * wl, 0, 1.0, 0.0, 0, stream)) return 1;
+  // V[m,q,i,j] = sum_{l,n} W[l,m,i,n] T1[n,q,j,l]
+  MixOpHost h;
+  h.rowptr.push_back(0);
+  const double* W = static_cast<const double*>(W_host);
+  for (int m = 0; m < wr; ++m)
+    for (int i = 0; i < d; ++i) {
+      for (int l = 0; l < wl; ++l)
+        for (int n = 0; n < d; ++n) {
+          double re, im = 0.0;
+          if (W) { const double* w = w_at(W, E, wr, d, l, m, i, n); re = w[0]; if (E == 2) im = w[1]; }
+          else { re = (l == m && i == n) ? 1.0 : 0.0; }
+          if (re == 0.0 && im == 0.0) continue;
+          h.in_off.push_back((long long)l + (long long)n * Dr * Dl * wl);
+          h.val.push_back(re); h.val.push_back(im);
+        }
+      h.rowptr.push_back((int)h.in_off.size());
+      h.out_off.push_back((long long)m * Dr * d * Dl + (long long)i * Dl);
+    }
+  PDMRG_REQUIRE(h.device_bytes() <= lay.op_bytes, "env_update_right: operator blob overflow");
+  MixOpDev dev;
+  if (upload_mix_op(h, op_dev, &dev, stream)) return 1;
+  if (launch_mix(dtype, dev, T1, V, Dr, Dl, (long long)Dl * wl, wl, (long long)d * Dl, 1, stream)) return 1;
+  // out[k,(m,q)] = sum_{(i,j)} AbT[k,(i,j)] V[(m,q),(i,j)]
+  if (pdmrg_gemm_nt(dtype, Dr, wr * Dr, d * Dl, 1, AbT, (long long)d * Dl, 0, V, (long long)d * Dl, 0, 0, out,
+                    (long long)wr * Dr, 0, 1.0, 0.0, 0, stream))
+    return 1;
+  return 0;
+}
+
+extern "C" int pdmrg_env_update_left(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                                     const void* R, const void* B, const void* Bbra, void* out,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "env_update_left: bad dtype");
+  if (!W_host) PDMRG_REQUIRE(wl == wr, "env_update_left: identity MPO entry needs wl == wr");
+  const EnvLayout lay = env_layout(dtype, d, Dl, Dr, wl, wr);
+  PDMRG_REQUIRE(workspace_bytes >= lay.total(), "env_update_left: workspace too small");
+  const int E = dtype == PDMRG_C128 ? 2 : 1;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  void* op_dev = ws;
+  double* BbT = reinterpret_cast<double*>(ws + lay.op_bytes);
+  double* T1 = reinterpret_cast<double*>(ws + lay.op_bytes + lay.pack_a + lay.pack_b);
+  double* V = reinterpret_cast<double*>(ws + lay.op_bytes + lay.pack_a + lay.pack_b + lay.t1);
+  // BbT[x,b,c] = Bbra[b,x,c]
+  if (pdmrg_permute4(dtype, Bbra ? Bbra : B, BbT, 1, Dl, d, Dr, 0, Dr, (long long)Dl * Dr, 1, Bbra ? 0 : 1, nullptr, 0, stream)) return 1;
+  // T1[(e,a),(c,dd)] = sum_f B[(e,a),f] R[(c,dd),f]
+  if (pdmrg_gemm_nt(dtype, d * Dl, Dr * wr, Dr, 1, B, Dr, 0, R, Dr, 0, 0, T1, (long long)Dr * wr, 0, 1.0, 0.0, 0, stream)) return 1;
+  // V[y,a,b,c] = sum_{dd,e} W[y,dd,b,e] T1[e,a,c,dd]
+  MixOpHost h;
+  h.rowptr.push_back(0);
+  const double* W = static_cast<const double*>(W_host);
+  for (int y = 0; y < wl; ++y)
+    for (int b = 0; b < d; ++b) {
+      for (int dd = 0; dd < wr; ++dd)
+        for (int e = 0; e < d; ++e) {
+          double re, im = 0.0;
+          if (W) { const double* w = w_at(W, E, wr, d, y, dd, b, e); re = w[0]; if (E == 2) im = w[1]; }
+          else { re = (y == dd && b == e) ? 1.0 : 0.0; }
+          if (re == 0.0 && im == 0.0) continue;
+          h.in_off.push_back((long long)dd + (long long)e * Dl * Dr * wr);
+          h.val.push_back(re); h.val.push_back(im);
+        }
+      h.rowptr.push_back((int)h.in_off.size());
+      h.out_off.push_back((long long)y * Dl * d * Dr + (long long)b * Dr);
+    }
+  PDMRG_REQUIRE(h.device_bytes() <= lay.op_bytes, "env_update_left: operator blob overflow");
+  MixOpDev dev;
+  if (upload_mix_op(h, op_dev, &dev, stream)) return 1;
+  if (launch_mix(dtype, dev, T1, V, Dl, Dr, (long long)Dr * wr, wr, (long long)d * Dr, 1, stream)) return 1;
+  // out[x,(y,a)] = sum_{(b,c)} BbT[x,(b,c)] V[(y,a),(b,c)]
+  if (pdmrg_gemm_nt(dtype, Dl, wl * Dl, d * Dr, 1, BbT, (long long)d * Dr, 0, V, (long long)d * Dr, 0, 0, out,
+                    (long long)wl * Dl, 0, 1.0, 0.0, 0, stream))
+    return 1;
+  return 0;
+}

@@ -1,0 +1,311 @@
+// HBM-bound vector kernels of the device-resident Davidson solver
+// (reference: pydmrg/tools/la_tools.py:449-457 projected-matrix dots, :469-470 Ritz
+// combination, :479-482 residual and norm, :524-536 projection against the basis).
+//
+// The Krylov basis and its images stay resident in HBM as two (max_space x n) slabs; every
+// kernel below makes ONE pass over the vectors it touches (all m dot products of a vector
+// against the basis share a single read of that vector; the residual, its norm and the
+// Ritz combination are fused).  Reductions are two-stage and ordered (per-block partials,
+// then a single-block tree), so results are bit-reproducible run to run.
+#include "common.cuh"
+
+namespace pdmrg {
+namespace {
+
+constexpr int VT = 256;        // threads per block
+constexpr int MAXM = 16;       // basis vectors handled per pass
+constexpr int MAX_BLOCKS = 148 * 4;
+
+struct Coefs {
+  double re[2 * MAXM + 2];
+  double im[2 * MAXM + 2];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-reduce `nv` doubles per thread (in vals[]) into partial[blockIdx.x * nv + i]
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&vals)[NV], int nv, double* partial) {
+  __shared__ double sm[VT / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const double s = warp_sum(vals[i]);
+      if (lane == 0) sm[warp][i] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < VT / 32; ++w) s += sm[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * nv + threadIdx.x] = s;
+  }
+}
+
+// out[i] = sum over blocks of partial[b*nv + i]   (single block, ordered)
+__global__ void __launch_bounds__(VT) final_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv,
+                                                          double* __restrict__ out) {
+  __shared__ double sm[VT];
+  for (int i = 0; i < nv; ++i) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += VT) s += partial[(size_t)b * nv + i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = VT / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[i] = sm[0];
+    __syncthreads();
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+dots_kernel(long long n, int m, const double* __restrict__ X, long long stride, const double* __restrict__ y,
+            double* __restrict__ partial) {
+  double acc[2 * MAXM];
+#pragma unroll
+  for (int i = 0; i < 2 * MAXM; ++i) acc[i] = 0.0;
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+    if (CPLX) {
+      const double2 yv = reinterpret_cast<const double2*>(y)[e];
+#pragma unroll
+      for (int i = 0; i < MAXM; ++i) {
+        if (i < m) {
+          const double2 xv = reinterpret_cast<const double2*>(X + 2 * i * stride)[e];
+          acc[2 * i] = fma(xv.x, yv.x, acc[2 * i]); acc[2 * i] = fma(xv.y, yv.y, acc[2 * i]);
+          acc[2 * i + 1] = fma(xv.x, yv.y, acc[2 * i + 1]); acc[2 * i + 1] = fma(-xv.y, yv.x, acc[2 * i + 1]);
+        }
+      }
+    } else {
+      const double yv = y[e];
+#pragma unroll
+      for (int i = 0; i < MAXM; ++i)
+        if (i < m) acc[i] = fma(X[i * stride + e], yv, acc[i]);
+    }
+  }
+  block_reduce_store<2 * MAXM>(acc, CPLX ? 2 * m : m, partial);
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+combine_kernel(long long n, int m, Coefs c, const double* __restrict__ X, long long stride,
+               double* __restrict__ out, int accumulate) {
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+    if (CPLX) {
+      double2 acc = accumulate ? reinterpret_cast<double2*>(out)[e] : make_double2(0.0, 0.0);
+      for (int i = 0; i < m; ++i)
+        cfma(acc, make_double2(c.re[i], c.im[i]), reinterpret_cast<const double2*>(X + 2 * i * stride)[e]);
+      reinterpret_cast<double2*>(out)[e] = acc;
+    } else {
+      double acc = accumulate ? out[e] : 0.0;
+      for (int i = 0; i < m; ++i) acc = fma(c.re[i], X[i * stride + e], acc);
+      out[e] = acc;
+    }
+  }
+}
+
+// r = sum_i v_i (AX_i - e XS_i); coefficient slot m holds e
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+residual_kernel(long long n, int m, Coefs c, const double* __restrict__ XS, const double* __restrict__ AX,
+                long long stride, double* __restrict__ r, int accumulate, double* __restrict__ partial) {
+  double nrm[1] = {0.0};
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+    if (CPLX) {
+      double2 ax = make_double2(0.0, 0.0), xs = make_double2(0.0, 0.0);
+      for (int i = 0; i < m; ++i) {
+        const double2 v = make_double2(c.re[i], c.im[i]);
+        cfma(ax, v, reinterpret_cast<const double2*>(AX + 2 * i * stride)[e]);
+        cfma(xs, v, reinterpret_cast<const double2*>(XS + 2 * i * stride)[e]);
+      }
+      const double2 ev = make_double2(c.re[2 * MAXM], c.im[2 * MAXM]);
+      double2 res = accumulate ? reinterpret_cast<double2*>(r)[e] : make_double2(0.0, 0.0);
+      res.x += ax.x - (ev.x * xs.x - ev.y * xs.y);
+      res.y += ax.y - (ev.x * xs.y + ev.y * xs.x);
+      reinterpret_cast<double2*>(r)[e] = res;
+      nrm[0] = fma(res.x, res.x, nrm[0]); nrm[0] = fma(res.y, res.y, nrm[0]);
+    } else {
+      double ax = 0.0, xs = 0.0;
+      for (int i = 0; i < m; ++i) { ax = fma(c.re[i], AX[i * stride + e], ax); xs = fma(c.re[i], XS[i * stride + e], xs); }
+      double res = (accumulate ? r[e] : 0.0) + ax - c.re[2 * MAXM] * xs;
+      r[e] = res;
+      nrm[0] = fma(res, res, nrm[0]);
+    }
+  }
+  block_reduce_store<1>(nrm, 1, partial);
+}
+
+// r = (r - sum_i c_i X_i) * s,  s = (1.0 / sqrt(scale[0])) if scale given on the LAST pass
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+project_kernel(long long n, int m, const double* __restrict__ X, long long stride, const double* __restrict__ cdev,
+               const double* __restrict__ scale, double* __restrict__ r, double* __restrict__ partial) {
+  const double s = scale ? (1.0 / sqrt(scale[0])) : 1.0;
+  double nrm[1] = {0.0};
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+    if (CPLX) {
+      double2 res = reinterpret_cast<double2*>(r)[e];
+      for (int i = 0; i < m; ++i) {
+        const double2 ci = make_double2(-cdev[2 * i], -cdev[2 * i + 1]);
+        cfma(res, ci, reinterpret_cast<const double2*>(X + 2 * i * stride)[e]);
+      }
+      res.x *= s; res.y *= s;
+      reinterpret_cast<double2*>(r)[e] = res;
+      nrm[0] = fma(res.x, res.x, nrm[0]); nrm[0] = fma(res.y, res.y, nrm[0]);
+    } else {
+      double res = r[e];
+      for (int i = 0; i < m; ++i) res = fma(-cdev[i], X[i * stride + e], res);
+      res *= s;
+      r[e] = res;
+      nrm[0] = fma(res, res, nrm[0]);
+    }
+  }
+  block_reduce_store<1>(nrm, 1, partial);
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+normalize_kernel(long long n, const double* __restrict__ in, const double* __restrict__ norm2, double* __restrict__ out) {
+  const double s = (1.0 / sqrt(norm2[0]));
+  const long long nd = CPLX ? 2 * n : n;
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < nd; e += (long long)gridDim.x * VT) out[e] = in[e] * s;
+}
+
+int vec_grid(long long n) {
+  long long b = (n + VT - 1) / VT;
+  const long long cap = (long long)num_sms() * 4 < MAX_BLOCKS ? (long long)num_sms() * 4 : MAX_BLOCKS;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+}  // namespace pdmrg
+
+using namespace pdmrg;
+
+extern "C" size_t pdmrg_vec_scratch_bytes(int m) {
+  (void)m;
+  return (size_t)MAX_BLOCKS * 2 * MAXM * sizeof(double) + 256;
+}
+
+extern "C" int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long long stride, const void* y,
+                              void* out_dev, void* scratch, size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(scratch_bytes >= pdmrg_vec_scratch_bytes(m), "pdmrg_vec_dots: scratch too small");
+  PDMRG_REQUIRE(n > 0 && m >= 0, "pdmrg_vec_dots: bad extents");
+  const bool cplx = dtype == PDMRG_C128;
+  const int E = cplx ? 2 : 1;
+  const int grid = vec_grid(n);
+  double* partial = static_cast<double*>(scratch);
+  for (int i0 = 0; i0 < m; i0 += MAXM) {
+    const int mm = (m - i0) < MAXM ? (m - i0) : MAXM;
+    const double* Xp = static_cast<const double*>(X) + (size_t)E * i0 * stride;
+    if (cplx) dots_kernel<true><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, (const double*)y, partial);
+    else dots_kernel<false><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, (const double*)y, partial);
+    PDMRG_CHECK_LAUNCH();
+    // complex: partial holds (re,im) pairs -> out is interleaved complex
+    final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, E * mm, static_cast<double*>(out_dev) + E * i0);
+    PDMRG_CHECK_LAUNCH();
+    count_launch(2);
+  }
+  return 0;
+}
+
+static int fill_coefs(Coefs& c, int dtype, const void* host, int m0, int m) {
+  const double* h = static_cast<const double*>(host);
+  for (int i = 0; i < m; ++i) {
+    if (dtype == PDMRG_C128) { c.re[i] = h[2 * (m0 + i)]; c.im[i] = h[2 * (m0 + i) + 1]; }
+    else { c.re[i] = h[m0 + i]; c.im[i] = 0.0; }
+  }
+  return 0;
+}
+
+extern "C" int pdmrg_vec_combine(int dtype, long long n, int m, const void* coef_host, const void* X,
+                                 long long stride, void* out, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(n > 0 && m > 0, "pdmrg_vec_combine: bad extents");
+  const bool cplx = dtype == PDMRG_C128;
+  const int E = cplx ? 2 : 1;
+  const int grid = vec_grid(n);
+  for (int i0 = 0; i0 < m; i0 += 2 * MAXM) {
+    const int mm = (m - i0) < 2 * MAXM ? (m - i0) : 2 * MAXM;
+    Coefs c;
+    fill_coefs(c, dtype, coef_host, i0, mm);
+    const double* Xp = static_cast<const double*>(X) + (size_t)E * i0 * stride;
+    const int acc = (accumulate || i0 > 0) ? 1 : 0;
+    if (cplx) combine_kernel<true><<<grid, VT, 0, stream>>>(n, mm, c, Xp, stride, (double*)out, acc);
+    else combine_kernel<false><<<grid, VT, 0, stream>>>(n, mm, c, Xp, stride, (double*)out, acc);
+    PDMRG_CHECK_LAUNCH();
+    count_launch();
+  }
+  return 0;
+}
+
+extern "C" int pdmrg_davidson_residual(int dtype, long long n, int m, const void* v_host, const void* e_host,
+                                       const void* XS, const void* AX, long long stride, void* r,
+                                       double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(scratch_bytes >= pdmrg_vec_scratch_bytes(m), "pdmrg_davidson_residual: scratch too small");
+  PDMRG_REQUIRE(n > 0 && m > 0, "pdmrg_davidson_residual: bad extents");
+  const bool cplx = dtype == PDMRG_C128;
+  const int E = cplx ? 2 : 1;
+  const int grid = vec_grid(n);
+  double* partial = static_cast<double*>(scratch);
+  const double* eh = static_cast<const double*>(e_host);
+  for (int i0 = 0; i0 < m; i0 += 2 * MAXM) {
+    const int mm = (m - i0) < 2 * MAXM ? (m - i0) : 2 * MAXM;
+    Coefs c;
+    fill_coefs(c, dtype, v_host, i0, mm);
+    c.re[2 * MAXM] = eh[0];
+    c.im[2 * MAXM] = cplx ? eh[1] : 0.0;
+    const double* XSp = static_cast<const double*>(XS) + (size_t)E * i0 * stride;
+    const double* AXp = static_cast<const double*>(AX) + (size_t)E * i0 * stride;
+    if (cplx) residual_kernel<true><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial);
+    else residual_kernel<false><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial);
+    PDMRG_CHECK_LAUNCH();
+    count_launch();
+  }
+  final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, 1, norm2_dev);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
+  return 0;
+}
+
+extern "C" int pdmrg_vec_project(int dtype, long long n, int m, const void* X, long long stride, const void* c_dev,
+                                 const double* scale_dev, void* r, double* norm2_dev, void* scratch,
+                                 size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(scratch_bytes >= pdmrg_vec_scratch_bytes(m), "pdmrg_vec_project: scratch too small");
+  PDMRG_REQUIRE(n > 0 && m >= 0, "pdmrg_vec_project: bad extents");
+  const bool cplx = dtype == PDMRG_C128;
+  const int grid = vec_grid(n);
+  double* partial = static_cast<double*>(scratch);
+  if (cplx) project_kernel<true><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial);
+  else project_kernel<false><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial);
+  PDMRG_CHECK_LAUNCH();
+  final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, 1, norm2_dev);
+  PDMRG_CHECK_LAUNCH();
+  count_launch(2);
+  return 0;
+}
+
+extern "C" int pdmrg_vec_normalize(int dtype, long long n, const void* in, const double* norm2_dev, void* out,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(n > 0, "pdmrg_vec_normalize: bad extent");
+  const int grid = vec_grid(dtype == PDMRG_C128 ? 2 * n : n);
+  if (dtype == PDMRG_C128) normalize_kernel<true><<<grid, VT, 0, stream>>>(n, (const double*)in, norm2_dev, (double*)out);
+  else normalize_kernel<false><<<grid, VT, 0, stream>>>(n, (const double*)in, norm2_dev, (double*)out);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
+  return 0;
+}

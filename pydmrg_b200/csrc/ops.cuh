@@ -1,0 +1,38 @@
+// Internal (non-ABI) interfaces between the pydmrg_b200 CUDA translation units.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace pdmrg {
+
+// Sparse "mixing" operator applied point-wise over a 2-D index space (x, y):
+//   out[row, x, y] = sum_{nz in row} val[nz] * in[col[nz], x, y]
+// Rows / columns are composite (MPO-bond, physical) indices whose memory offsets are
+// pre-resolved on the host, so one kernel serves every W-application of the hot path
+// (tools/diag_tools.py:118,154-155; tools/env_tools.py:36,48).
+struct MixOpHost {
+  std::vector<int> rowptr;            // rows+1
+  std::vector<long long> in_off;      // per nz: element offset of the input slab
+  std::vector<double> val;            // per nz: (re, im) pairs (im ignored for f64)
+  std::vector<long long> out_off;     // per row: element offset of the output slab
+  int rows() const { return (int)rowptr.size() - 1; }
+  int nnz() const { return (int)in_off.size(); }
+  size_t device_bytes() const;
+};
+
+struct MixOpDev {
+  const int* rowptr;
+  const long long* in_off;
+  const double* val;
+  const long long* out_off;
+  int rows;
+};
+
+// copies the operator into `dst` (device, >= device_bytes()) on `stream`
+int upload_mix_op(const MixOpHost& h, void* dst, MixOpDev* dev, cudaStream_t stream);
+
+// in/out strides (elements) of the point-wise index space; y is the fastest thread index
+int launch_mix(int dtype, const MixOpDev& op, const void* in, void* out, int nx, int ny,
+               long long six, long long siy, long long sox, long long soy, cudaStream_t stream);
+
+}  // namespace pdmrg

@@ -1,0 +1,299 @@
+"""GPU parity tests of the CUDA kernels, called through the C ABI (pydmrg_b200._lib / .device),
+against the NumPy oracle (oracle/dmrg_oracle.py) and the golden fixtures generated from the
+unmodified reference (tests/golden/*.npz).
+
+Tolerances: the contractions are pure sums of products -> 1e-13 relative (norm-wise)
+(BASELINE.md section 4); singular values 1e-12 relative to the largest one."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+
+
+def rel(a, b):
+    a = np.asarray(a).ravel(); b = np.asarray(b).ravel()
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def crand(rng, *s):
+    return rng.standard_normal(s) + 1j * rng.standard_normal(s)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def D():
+    from pydmrg_b200 import device
+    return device
+
+
+@pytest.fixture(scope="module")
+def ws(D):
+    return D.Workspace(torch.device("cuda"))
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 192, 1000), (130, 70, 33), (64, 64, 64), (1, 1, 1),
+                                   (3, 5, 2), (200, 64, 8), (129, 257, 130), (512, 384, 96)])
+def test_gemm_nt_shapes(D, cplx, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    mk = (lambda *s: crand(rng, *s)) if cplx else (lambda *s: rng.standard_normal(s))
+    A, B = mk(M, K), mk(N, K)
+    C = D.gemm_nt(dev(A), dev(B))
+    torch.cuda.synchronize()
+    assert rel(C.cpu().numpy(), A @ B.T) < TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gemm_nt_paths_agree(D, cplx):
+    """TMA/DMMA path and the generic kernel give the same numbers; path selection is visible."""
+    rng = np.random.default_rng(5)
+    mk = (lambda *s: crand(rng, *s)) if cplx else (lambda *s: rng.standard_normal(s))
+    A, B = mk(192, 80), mk(160, 80)
+    C1 = D.gemm_nt(dev(A), dev(B))
+    assert D.lib.pdmrg_last_gemm_path() == 1
+    D.lib.pdmrg_set_force_generic_gemm(1)
+    try:
+        C2 = D.gemm_nt(dev(A), dev(B))
+        assert D.lib.pdmrg_last_gemm_path() == 2
+    finally:
+        D.lib.pdmrg_set_force_generic_gemm(0)
+    torch.cuda.synchronize()
+    assert rel(C1.cpu().numpy(), A @ B.T) < TOL and rel(C2.cpu().numpy(), A @ B.T) < TOL
+
+
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_gemm_nt_options(D, force_generic):
+    """conjB, complex alpha, beta=1 accumulation, batch with broadcast A, leading dimensions."""
+    rng = np.random.default_rng(11)
+    D.lib.pdmrg_set_force_generic_gemm(force_generic)
+    try:
+        M, N, K, nb = 96, 72, 40, 3
+        A = crand(rng, M, K + 8)          # lda = K+8
+        B = crand(rng, nb, N, K)
+        C0 = crand(rng, nb, M, N + 4)     # ldc = N+4
+        Cd = dev(C0)
+        alpha = 0.7 - 0.3j
+        D.gemm_nt(dev(A), dev(B), Cd, M=M, N=N, K=K, batch=nb, lda=K + 8, ldb=K, ldc=N + 4, strideA=0,
+                  strideB=N * K, strideC=M * (N + 4), conjB=True, alpha=alpha, beta=1)
+        torch.cuda.synchronize()
+        ref = C0.copy()
+        for b in range(nb):
+            ref[b, :, :N] += alpha * (A[:, :K] @ B[b].conj().T)
+        assert rel(Cd.cpu().numpy(), ref) < TOL
+        # real, odd leading dimension (not 16-byte aligned rows) must still be right
+        Ar, Br = rng.standard_normal((70, 33)), rng.standard_normal((50, 33))
+        Cr = D.gemm_nt(dev(Ar), dev(Br), alpha=-1.0)
+        torch.cuda.synchronize()
+        assert rel(Cr.cpu().numpy(), -(Ar @ Br.T)) < TOL
+    finally:
+        D.lib.pdmrg_set_force_generic_gemm(0)
+
+
+def test_permute4(D):
+    rng = np.random.default_rng(3)
+    a = crand(rng, 3, 4, 5, 6)
+    out = torch.empty((6, 4, 3, 5), dtype=torch.complex128, device="cuda")
+    sc = dev(rng.standard_normal(4))
+    # out[i3,i1,i0,i2] = conj(a[i0,i1,i2,i3]) * sc[i1]
+    D.permute4(dev(a), out, (6, 4, 3, 5), (1, 30, 120, 6), conj=True, scale=sc, scale_axis=1)
+    torch.cuda.synchronize()
+    ref = np.conj(a).transpose(3, 1, 0, 2) * sc.cpu().numpy()[None, :, None, None]
+    assert rel(out.cpu().numpy(), ref) < 1e-15
+
+
+# ---------------------------------------------------------------------------------------
+def _heff(D, ws, x, Ls, Wcs, Rs, P, Dl, Dr, code):
+    plan = D.HeffPlan(code, P, Dl, Dr, [(dev(L), Wc, dev(R)) for L, Wc, R in zip(Ls, Wcs, Rs)], ws)
+    xd = dev(x.reshape(-1))
+    yd = torch.empty_like(xd)
+    plan.apply(xd, yd, -1.0)
+    torch.cuda.synchronize()
+    return yd.cpu().numpy(), plan
+
+
+@pytest.mark.parametrize("c", ["a", "b", "c", "d"])
+def test_heff_golden(D, ws, golden, c):
+    """H1 and H2 against reference outputs (tools/diag_tools.py:108-125, 146-162)."""
+    g = golden["kernels"]
+    L, R, W1, W2 = g[c + "_L"], g[c + "_R"], g[c + "_W1"], g[c + "_W2"]
+    x1, x2 = g[c + "_x1"], g[c + "_x2"]
+    d, Dl, Dr = x1.shape
+    w = W1.shape[0]
+    y1, _ = _heff(D, ws, x1, [L], [D.combine_onesite(W1, w, w, d, np.complex128)], [R], d, Dl, Dr, D.C128)
+    assert rel(y1, g[c + "_y1"]) < TOL
+    y2, plan = _heff(D, ws, x2, [L], [D.combine_twosite(W1, W2, np.complex128)], [R], d * d, Dl, Dr, D.C128)
+    assert rel(y2, g[c + "_y2"]) < TOL
+    assert plan.flops_sparse <= plan.flops_dense
+
+
+@pytest.mark.parametrize("chi,real", [(64, False), (96, False), (128, True), (160, False)])
+def test_heff_vs_oracle_large(D, ws, chi, real):
+    """TMA/DMMA tile path at sizes the oracle finishes in seconds; ASEP and Heisenberg W."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import mpo as M
+    rng = np.random.default_rng(chi)
+    d = 2
+    Dl, Dr = chi, chi - 8
+    if real:
+        W1, W2 = M.heisenberg_mpo(6)[0][2:4]
+        mk = lambda *s: rng.standard_normal(s)
+        code, npdt = D.F64, np.float64
+    else:
+        W1, W2 = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))[0][2:4]
+        mk = lambda *s: crand(rng, *s)
+        code, npdt = D.C128, np.complex128
+    w = W1.shape[0]
+    L, R = mk(Dl, w, Dl), mk(Dr, w, Dr)
+    x2 = mk(d, d, Dl, Dr)
+    y2, plan = _heff(D, ws, x2, [L], [D.combine_twosite(W1, W2, npdt)], [R], d * d, Dl, Dr, code)
+    ref = orc.heff_twosite(x2.reshape(-1), [L], [W1], [W2], [R], x2.shape)
+    assert rel(y2, ref) < TOL
+    x1 = mk(d, Dl, Dr)
+    y1, _ = _heff(D, ws, x1, [L, L], [D.combine_onesite(W1, w, w, d, npdt)] * 2, [R, R], d, Dl, Dr, code)
+    ref1 = 2 * orc.heff_onesite(x1.reshape(-1), [L], [W1], [R], x1.shape)
+    assert rel(y1, ref1) < TOL
+
+
+def test_heff_linearity_full_size(D, ws):
+    """Size-independent property at a large bond (chi=512): H(a x + b y) = a Hx + b Hy, and
+    MPO-bond-sharded partial sums add up to the full result."""
+    from pydmrg_b200 import mpo as M
+    chi = 512
+    W1, W2 = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))[0][2:4]
+    Wc = D.combine_twosite(W1, W2, np.complex128)
+    torch.manual_seed(0)
+    L = torch.randn(chi, 6, chi, dtype=torch.complex128, device="cuda")
+    R = torch.randn(chi, 6, chi, dtype=torch.complex128, device="cuda")
+    plan = D.HeffPlan(D.C128, 4, chi, chi, [(L, Wc, R)], ws)
+    n = 4 * chi * chi
+    x = torch.randn(n, dtype=torch.complex128, device="cuda")
+    y = torch.randn(n, dtype=torch.complex128, device="cuda")
+    a, b = 0.3 - 1.1j, -0.8 + 0.2j
+    hx, hy, hz = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    plan.apply(x, hx); plan.apply(y, hy); plan.apply(a * x + b * y, hz)
+    torch.cuda.synchronize()
+    err = (hz - (a * hx + b * hy)).norm() / hz.norm()
+    assert err.item() < 1e-13
+    mask0 = np.zeros((6, 6), dtype=np.uint8); mask0[:, 0] = 1
+    mask1 = 1 - mask0
+    p0 = D.HeffPlan(D.C128, 4, chi, chi, [(L, Wc, R)], ws, block_masks=[mask0])
+    p1 = D.HeffPlan(D.C128, 4, chi, chi, [(L, Wc, R)], ws, block_masks=[mask1])
+    y0, y1 = torch.empty_like(x), torch.empty_like(x)
+    p0.apply(x, y0); p1.apply(x, y1)
+    torch.cuda.synchronize()
+    assert ((y0 + y1) - hx).norm().item() / hx.norm().item() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", ["a", "b", "c", "d"])
+def test_env_updates_golden(D, ws, golden, c):
+    """E1/E2 against reference update_envR / update_envL outputs (tools/env_tools.py:28-50)."""
+    g = golden["kernels"]
+    A, W, L, R, Abra = g[c + "_A"], g[c + "_W1"].astype(np.complex128), g[c + "_L"], g[c + "_R"], g[c + "_Abra"]
+    out = D.env_update_right(dev(A), W, dev(L), None, ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), g[c + "_envR_out"]) < TOL
+    out = D.env_update_left(dev(A), W, dev(R), None, ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), g[c + "_envL_out"]) < TOL
+    out = D.env_update_right(dev(A), W, dev(L), dev(Abra), ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), g[c + "_envR_bra_out"]) < TOL
+    out = D.env_update_left(dev(A), None, dev(R), dev(Abra), ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), g[c + "_envL_none_out"]) < TOL
+
+
+@pytest.mark.parametrize("real", [False, True])
+def test_env_updates_large(D, ws, real):
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import mpo as M
+    rng = np.random.default_rng(17)
+    d, Dl, Dr = 2, 144, 120
+    if real:
+        W = M.heisenberg_mpo(6)[0][2]; mk = lambda *s: rng.standard_normal(s)
+    else:
+        W = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))[0][2].astype(np.complex128); mk = lambda *s: crand(rng, *s)
+    w = W.shape[0]
+    A, L, R = mk(d, Dl, Dr), mk(Dl, w, Dl), mk(Dr, w, Dr)
+    out = D.env_update_right(dev(A), W, dev(L), None, ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), orc.env_update_right(A, W, L)) < TOL
+    out = D.env_update_left(dev(A), W, dev(R), None, ws)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), orc.env_update_left(A, W, R)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("real", [False, True])
+def test_vec_ops(D, real):
+    rng = np.random.default_rng(23)
+    n, m = 70001, 19
+    mk = (lambda *s: rng.standard_normal(s)) if real else (lambda *s: crand(rng, *s))
+    code = D.F64 if real else D.C128
+    X, AX, y = mk(m, n), mk(m, n), mk(n)
+    v, e = mk(m), mk(1)[0]
+    ops = D.VecOps(code, n, torch.device("cuda"))
+    Xd, AXd, yd = dev(X), dev(AX), dev(y)
+    dots = ops.dots(Xd, m, yd)
+    torch.cuda.synchronize()
+    assert rel(dots[:m].cpu().numpy(), X.conj() @ y) < 1e-13
+    out = torch.empty_like(yd)
+    ops.combine(v, Xd, m, out)
+    torch.cuda.synchronize()
+    assert rel(out.cpu().numpy(), v @ X) < 1e-13
+    r = torch.empty_like(yd)
+    nrm = ops.residual(v, e, Xd, AXd, m, r)
+    torch.cuda.synchronize()
+    rr = v @ AX - e * (v @ X)
+    assert rel(r.cpu().numpy(), rr) < 1e-13
+    assert abs(nrm[0].item() - np.vdot(rr, rr).real) < 1e-12 * np.vdot(rr, rr).real
+    c = ops.dots(Xd, m, r)
+    n2 = ops.project(Xd, m, c, r, scale_dev=nrm)
+    torch.cuda.synchronize()
+    ref = (rr - (X.conj() @ rr) @ X) / np.sqrt(np.vdot(rr, rr).real)
+    assert rel(r.cpu().numpy(), ref) < 1e-12
+    assert abs(n2[0].item() - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
+    ops.normalize(r, n2, r)
+    torch.cuda.synchronize()
+    assert abs(np.linalg.norm(r.cpu().numpy()) - 1) < 1e-13
+
+
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("real", [False, True])
+@pytest.mark.parametrize("shape", [(64, 64), (48, 96), (96, 48), (2, 4), (1, 2), (200, 200)])
+def test_svd(D, ws, method, real, shape):
+    rng = np.random.default_rng(shape[0] * 13 + shape[1])
+    a = rng.standard_normal(shape) if real else crand(rng, *shape)
+    U, S, Vh, info = D.svd(dev(a.copy()), ws, method)
+    torch.cuda.synchronize()
+    assert info.item() == 0
+    U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+    Sref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(S - Sref)) < 1e-12 * Sref[0]
+    assert rel((U * S) @ Vh, a) < 1e-12
+    k = min(shape)
+    assert np.allclose(U.conj().T @ U, np.eye(k), atol=1e-11) and np.allclose(Vh @ Vh.conj().T, np.eye(k), atol=1e-11)
+
+
+@pytest.mark.parametrize("real", [False, True])
+def test_heevd(D, ws, real):
+    rng = np.random.default_rng(2)
+    n = 96
+    m = rng.standard_normal((n, 40)) if real else crand(rng, n, 40)
+    rho = m @ m.conj().T
+    w, vecs, info = D.heevd(dev(rho.copy()), ws)
+    torch.cuda.synchronize()
+    assert info.item() == 0
+    w, vecs = w.cpu().numpy(), vecs.cpu().numpy()
+    assert np.allclose(w, np.linalg.eigvalsh(rho), atol=1e-11 * abs(w).max())
+    # row i of vecs is eigenvector i:  rho v = w v
+    assert rel(rho @ vecs.T, vecs.T * w) < 1e-11
