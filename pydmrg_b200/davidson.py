@@ -1,0 +1,197 @@
+"""Device-resident restarted non-symmetric Davidson.
+
+Mirrors the algorithm the reference runs for every local eigenproblem
+(``davidson_nosym1``, pydmrg/tools/la_tools.py:402-557, called from
+pydmrg/tools/diag_tools.py:260 with the identity preconditioner, ``pick_eigs``,
+``tol=1e-16, max_cycle=1000, follow_state=False``): same subspace growth, same restart rule
+(``space + nroots > max_space``, la_tools.py:544, with max_space = 12 + 3*nroots, :412), same
+linear-dependence pruning (``lindep``, :505-537) -- which is what actually terminates the
+reference's loop, because its convergence flags are never set (:485-488).
+
+What is different is where the work happens: the basis ``xs`` and its images ``ax`` are two
+HBM-resident (max_space+nroots, n) slabs, the mat-vec is the DMMA H_eff plan, and every
+vector operation is one fused pass of a CUDA kernel (csrc/krylov.cu).  The host only solves
+the (<= 15+) x (<= 15+) projected eigenproblem with ``scipy.linalg.eig`` -- exactly the call the
+reference makes (la_tools.py:461) -- and reads back O(m) scalars twice per cycle.
+
+The in-loop orthogonalisation is block classical Gram-Schmidt (one multi-dot pass + one
+multi-axpy pass) instead of the reference's sequential modified Gram-Schmidt (:524-527);
+both project the same residual against the same orthonormal basis and agree to rounding.
+"""
+import numpy as np
+import scipy.linalg as sla
+import torch
+
+from . import device as D
+
+
+def pick_lowest_real(w, v):
+    """pick_eigs, pydmrg/tools/diag_tools.py:175-179: ascending real part."""
+    idx = np.argsort(np.real(w))
+    return w[idx], v[:, idx]
+
+
+class DavidsonWorkspace:
+    """Basis slabs + scratch for vectors of length <= n (re-used across sites)."""
+
+    def __init__(self, code, n, rows, nroots, device):
+        self.code, self.n, self.rows, self.nroots = code, n, rows, nroots
+        dt = D.torch_dtype(code)
+        self.XS = torch.empty((rows, n), dtype=dt, device=device)
+        self.AX = torch.empty((rows, n), dtype=dt, device=device)
+        self.R = torch.empty((2 * nroots + 2, n), dtype=dt, device=device)   # residual / Ritz vectors
+        self.small = torch.zeros(2 * rows * (nroots + 2) + 16, dtype=dt, device=device)
+        self.norms = torch.zeros(2 * nroots + 16, dtype=torch.float64, device=device)
+        self._ops = {}
+
+    def ops(self, n):
+        o = self._ops.get(n)
+        if o is None:
+            if len(self._ops) > 8:
+                self._ops.clear()
+            o = D.VecOps(self.code, n, self.XS.device)
+            self._ops[n] = o
+        return o
+
+
+_WS_CACHE = {}
+
+
+def get_workspace(code, n, rows, nroots, device):
+    key = (code, str(device))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.n < n or ws.rows < rows or ws.nroots < nroots:
+        _WS_CACHE.pop(key, None)
+        ws = None     # free the old slabs before allocating the new ones
+        ws = DavidsonWorkspace(code, n, rows, nroots, device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def release_workspaces():
+    _WS_CACHE.clear()
+
+
+def _orthonormalise(ops, src, dst, norm_slot, small):
+    """Gram-Schmidt of a short list of device vectors (la_tools.py:586-598) into ``dst``."""
+    out = []
+    for s, d in zip(src, dst):
+        if d.data_ptr() != s.data_ptr():
+            d.copy_(s)
+        if not out:
+            ops.project(d.unsqueeze(0), 0, small, d, scale_dev=None, norm2_out=norm_slot)   # m = 0: norm only
+        for u in out:
+            c = ops.dots(u.unsqueeze(0), 1, d, out=small)
+            ops.project(u.unsqueeze(0), 1, c, d, scale_dev=None, norm2_out=norm_slot)
+        ops.normalize(d, norm_slot, d)
+        out.append(d)
+    return out
+
+
+def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
+             res_tol=None, fixed_cycles=None, stats=None):
+    """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
+    (y <- A x, both device vectors of length n).
+
+    x0: list of device vectors (initial guesses).  Returns (e ndarray (k,), [k device vectors]).
+    ``res_tol``: optional residual-norm stop; default is the reference's effective criterion,
+    ||r||^2 <= lindep.  ``fixed_cycles``: stop after exactly that many cycles (benchmarking).
+    """
+    if not isinstance(x0, (list, tuple)):
+        x0 = [x0]
+    x0 = list(x0)
+    max_space = max_space + 3 * nroots
+    rows = max_space + nroots
+    W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
+    ops = W.ops(n)
+    XS, AX = W.XS[:, :n], W.AX[:, :n]
+    heff = np.zeros((rows, rows), dtype=np.complex128)
+    thresh2 = lindep if res_tol is None else res_tol * res_tol
+    small_tail = W.small[-8:]
+    gs_norm = W.norms[-2:-1]
+
+    n_mv = 0
+    space = 0
+    fresh = True
+    e = v = None
+    trial = []
+    dx2 = np.zeros(1)
+    cyc = 0
+    for cyc in range(max_cycle):
+        if fresh:
+            space = 0
+            trial = _orthonormalise(ops, x0, [XS[k] for k in range(len(x0))], gs_norm, small_tail)
+        elif len(trial) > 1:
+            trial = _orthonormalise(ops, trial, trial, gs_norm, small_tail)
+        rnow = len(trial)
+        head = space
+        for k, tv in enumerate(trial):
+            if tv.data_ptr() != XS[head + k].data_ptr():
+                XS[head + k].copy_(tv)
+            matvec(XS[head + k], AX[head + k])
+            n_mv += 1
+        space = head + rnow
+        # projected matrix (la_tools.py:449-457): new columns <xs_i|A xt_k>, i < space, and new
+        # rows <xt_k|A xs_i> = conj <A xs_i|xt_k>, i < head -- two multi-dot passes per new vector
+        for k in range(rnow):
+            ops.dots(W.XS, space, AX[head + k], out=W.small[k * 2 * rows:])
+            if head > 0:
+                ops.dots(W.AX, head, XS[head + k], out=W.small[k * 2 * rows + rows:])
+        host = W.small[:rnow * 2 * rows].cpu().numpy()            # D2H #1 of the cycle
+        for k in range(rnow):
+            heff[:space, head + k] = host[k * 2 * rows: k * 2 * rows + space]
+            if head > 0:
+                heff[head + k, :head] = np.conj(host[k * 2 * rows + rows: k * 2 * rows + rows + head])
+        w, vv = sla.eig(heff[:space, :space])                      # la_tools.py:461
+        w, vv = pick_lowest_real(w, vv)
+        e = w[:nroots].copy()
+        v = vv[:, :nroots].copy()
+        if code == D.F64:
+            e, v = _force_real(e, v)
+        nr = e.shape[0]
+        # residual r_k = sum_i v_ik (A xs_i - e_k xs_i) and its norm (la_tools.py:479-482), then --
+        # with no host round trip in between -- projection against the basis and the new norm
+        for k in range(nr):
+            ops.residual(v[:, k], e[k], W.XS, W.AX, space, W.R[k][:n], norm2_out=W.norms[2 * k:2 * k + 1])
+            c = ops.dots(W.XS, space, W.R[k][:n])
+            ops.project(W.XS, space, c, W.R[k][:n], scale_dev=W.norms[2 * k:2 * k + 1],
+                        norm2_out=W.norms[2 * k + 1:2 * k + 2])
+        nrm = W.norms[:2 * nr].cpu().numpy()                       # D2H #2 of the cycle
+        dx2, px2 = nrm[0::2], nrm[1::2]
+        if stats is not None:
+            stats.setdefault("res_history", []).append(float(np.sqrt(dx2.max())))
+        trial = []
+        for k in range(nr):
+            if dx2[k] > thresh2 and px2[k] > lindep:               # la_tools.py:505-537
+                ops.normalize(W.R[k][:n], W.norms[2 * k + 1:2 * k + 2], W.R[k][:n])
+                trial.append(W.R[k][:n])
+        if not trial:                                              # la_tools.py:539-541
+            break
+        if fixed_cycles is not None and cyc + 1 >= fixed_cycles:
+            break
+        fresh = space + nroots > max_space                         # la_tools.py:544
+        if fresh:
+            x0 = [W.R[nr + k][:n] for k in range(nr)]
+            for k in range(nr):
+                ops.combine(v[:, k], W.XS, space, x0[k])
+    out = []
+    for k in range(e.shape[0]):
+        o = torch.empty(n, dtype=W.XS.dtype, device=W.XS.device)
+        ops.combine(v[:, k], W.XS, space, o)                       # Ritz vector, la_tools.py:469
+        out.append(o)
+    if stats is not None:
+        stats["n_matvec"] = stats.get("n_matvec", 0) + n_mv
+        stats["cycles"] = stats.get("cycles", 0) + cyc + 1
+        stats["last_residual"] = float(np.sqrt(dx2.max()))
+    return e, out
+
+
+def _force_real(e, v):
+    """f64 mode: the targeted Ritz pairs must be real (symmetric / Perron-Frobenius problems)."""
+    scale = max(1.0, float(np.max(np.abs(e.real))))
+    if np.max(np.abs(e.imag)) > 1e-9 * scale:
+        raise ArithmeticError("f64 Davidson met a complex Ritz value %r; run with dtype='c128'" % (e,))
+    piv = np.argmax(np.abs(v), axis=0)
+    ph = v[piv, np.arange(v.shape[1])]
+    v = v * (np.conj(ph) / np.abs(ph))
+    return e.real.astype(np.complex128), np.real(v).astype(np.complex128)

@@ -217,6 +217,12 @@ class VecOps:
         self.norm2 = torch.zeros(2, dtype=torch.float64, device=device)
         self.coefs = torch.zeros(128, dtype=self.dt, device=device)
 
+    def _host(self, a):
+        a = np.asarray(a)
+        if self.code == F64 and np.iscomplexobj(a):
+            a = a.real
+        return np.ascontiguousarray(a, dtype=self.npdt)
+
     def dots(self, X, m, y, out=None):
         """out[i] = <X_i|y>, i < m;  X is a (rows, n) slab.  Result stays on the device."""
         out = self.coefs if out is None else out
@@ -225,19 +231,20 @@ class VecOps:
         return out
 
     def combine(self, coef, X, m, out, accumulate=False):
-        c = np.ascontiguousarray(coef, dtype=self.npdt)
+        c = self._host(coef)
         check(lib.pdmrg_vec_combine(self.code, self.n, m, ctypes.c_void_p(c.ctypes.data), _ptr(X), X.stride(0),
                                     _ptr(out), int(accumulate), _stream()), "pdmrg_vec_combine")
         return out
 
-    def residual(self, v, e, XS, AX, m, r):
-        vv = np.ascontiguousarray(v, dtype=self.npdt)
-        ee = np.ascontiguousarray([e], dtype=self.npdt)
+    def residual(self, v, e, XS, AX, m, r, norm2_out=None):
+        norm2_out = self.norm2 if norm2_out is None else norm2_out
+        vv = self._host(v)
+        ee = self._host([e])
         check(lib.pdmrg_davidson_residual(self.code, self.n, m, ctypes.c_void_p(vv.ctypes.data),
                                           ctypes.c_void_p(ee.ctypes.data), _ptr(XS), _ptr(AX), XS.stride(0), _ptr(r),
-                                          _ptr(self.norm2), _ptr(self.scratch), self.scratch.numel(), _stream()),
+                                          _ptr(norm2_out), _ptr(self.scratch), self.scratch.numel(), _stream()),
               "pdmrg_davidson_residual")
-        return self.norm2
+        return norm2_out
 
     def project(self, X, m, c_dev, r, scale_dev=None, norm2_out=None):
         norm2_out = self.norm2[1:] if norm2_out is None else norm2_out

@@ -1,0 +1,212 @@
+"""Local eigenproblem of a DMRG step on the device -- the replacement of
+pydmrg/tools/diag_tools.py (make_ham_func :106-171, calc_eigs :292-313, calc_eigs_davidson
+:243-290, calc_eigs_exact :193-212, calc_eigs_arnoldi :214-241, check_overlap :71-104).
+
+Conventions kept from the reference:
+  * ``Hfun(x)`` returns  -H_eff x  (diag_tools.py:125,162); the solver looks for the smallest
+    real part and the sign is flipped back, so the state with the LARGEST Re(E) is targeted;
+  * one-site guess = current site tensor (:255), two-site guess = einsum('ijk,lkm->iljm') (:257);
+  * for one root ``E`` is a scalar and ``vecs`` has shape (n, 1) after check_overlap;
+  * at the chain ends ``preserveState`` is forced on (:288) and, if no eigenvector overlaps
+    the guess by more than 0.98, the old guess is kept (:93-97).
+"""
+import numpy as np
+import scipy.linalg as sla
+import torch
+
+from . import device as D
+from .core import default_context, is_dev, like
+from .davidson import davidson
+
+
+def _site_ops(M, W, F, site, oneSite, ctx):
+    """Collect (L, Wc, R) per MPO term and the local problem shape."""
+    if oneSite:
+        d, Dl, Dr = M[site].shape
+        P = d
+        shape = (d, Dl, Dr)
+    else:
+        d1, Dl, _ = M[site].shape
+        d2, _, Dr = M[site + 1].shape
+        P = d1 * d2
+        shape = (d1, d2, Dl, Dr)
+    ops = []
+    for m in range(len(W)):
+        L = ctx.dev(F[m][site])
+        if oneSite:
+            R = ctx.dev(F[m][site + 1])
+            Wc = D.combine_onesite(W[m][site], L.shape[1], R.shape[1], shape[0], ctx.npdtype)
+        else:
+            # finite chains: right block of the bond is F[site+2]; the iDMRG two-slot list
+            # [L, R] (tools/env_tools.py:74-75) is addressed as F[site+1] by the reference
+            R = ctx.dev(F[m][site + 2] if len(F[m]) > site + 2 else F[m][site + 1])
+            W1, W2 = W[m][site], W[m][site + 1]
+            if W1 is None and W2 is None:
+                continue                                         # diag_tools.py:150-151
+            if W1 is None:
+                W1 = np.einsum("ab,ij->abij", np.eye(L.shape[1]), np.eye(shape[0]))
+            if W2 is None:
+                W2 = np.einsum("ab,ij->abij", np.eye(R.shape[1]), np.eye(shape[1]))
+            Wc = D.combine_twosite(W1, W2, ctx.npdtype)
+        ops.append((L, Wc, R))
+    return ops, P, shape
+
+
+def make_plan(M, W, F, site, oneSite=True, ctx=None, block_masks=None):
+    ctx = ctx or default_context()
+    ops, P, shape = _site_ops(M, W, F, site, oneSite, ctx)
+    Dl, Dr = shape[-2], shape[-1]
+    return D.HeffPlan(ctx.code, P, Dl, Dr, ops, ctx.ws, block_masks=block_masks), shape
+
+
+def make_ham_func(M, W, F, site, usePrecond=False, debug=False, oneSite=True, ctx=None):
+    """Returns (Hfun, precond) with the reference's closure contract (diag_tools.py:106-171):
+    ``Hfun(x)`` maps a flat vector (ndarray -> ndarray, or CUDA tensor -> CUDA tensor) to -H x."""
+    ctx = ctx or default_context()
+    plan, shape = make_plan(M, W, F, site, oneSite, ctx)
+
+    def Hfun(x):
+        xd = ctx.dev(x).reshape(-1)
+        yd = torch.empty_like(xd)
+        plan.apply(xd, yd, -1.0)
+        return like(yd, x)
+
+    def precond(dx, e, x0):                                   # diag_tools.py:137-139 (identity)
+        return dx
+
+    Hfun.plan = plan
+    return Hfun, precond
+
+
+def two_site_guess(A, B, ctx):
+    """theta[i,l,j,m] = sum_k A[i,j,k] B[l,k,m]   (diag_tools.py:257) as d1 batched NT GEMMs."""
+    d1, Dl, Dm = A.shape
+    d2, _, Dr = B.shape
+    Bt = ctx.empty(d2, Dr, Dm)
+    D.permute4(B, Bt, (d2, Dr, Dm), (Dm * Dr, 1, Dr))
+    theta = ctx.empty(d1, d2, Dl, Dr)
+    for i in range(d1):
+        D.gemm_nt(A[i], Bt, theta[i], M=Dl, N=Dr, K=Dm, batch=d2, lda=Dm, ldb=Dm, ldc=Dr,
+                  strideA=0, strideB=Dr * Dm, strideC=Dl * Dr)
+    return theta
+
+
+def check_overlap(guess, vecs, E, preserveState, ctx):
+    """diag_tools.py:71-104 with device vectors.  vecs: list of device vectors."""
+    ops = D.VecOps(ctx.code, guess.numel(), ctx.device) if not hasattr(ctx, "_ovl_ops") or ctx._ovl_ops.n != guess.numel() else ctx._ovl_ops
+    ctx._ovl_ops = ops
+    slab = torch.stack(vecs) if len(vecs) > 1 else vecs[0].unsqueeze(0)
+    ov = np.abs(ops.dots(slab, len(vecs), guess)[:len(vecs)].cpu().numpy())      # |<v_j|guess>|
+    matched = False
+    E = np.atleast_1d(np.asarray(E)).copy()
+    for j in range(len(vecs)):
+        if ov[j] > 0.98:
+            matched = True
+            if j != 0 and preserveState:
+                vecs[0], vecs[j] = vecs[j], vecs[0]
+                E[0], E[j] = E[j], E[0]
+                ov[0], ov[j] = ov[j], ov[0]
+    if preserveState and not matched:
+        vecs = [guess.clone()]
+        ov = np.abs(ops.dots(guess.unsqueeze(0), 1, guess)[:1].cpu().numpy())
+    return E, vecs, float(ov[0])
+
+
+def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
+              orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
+              fixed_cycles=None, return_device=None, plan=None):
+    """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
+    array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise."""
+    ctx = ctx or default_context()
+    own_plan = plan is None
+    if own_plan:
+        plan, shape = make_plan(mpsL[0], W, F, site, oneSite, ctx)
+    n = plan.n
+    dev_in = is_dev(mpsL[0][site]) if return_device is None else return_device
+    guesses = []
+    nS = min(nStates, n - 1) if n > 1 else 1
+    for s in range(nS):
+        if oneSite:
+            guesses.append(ctx.dev(mpsL[s][site]).reshape(-1))
+        else:
+            guesses.append(two_site_guess(ctx.dev(mpsL[s][site]), ctx.dev(mpsL[s][site + 1]), ctx).reshape(-1))
+    if alg == "davidson":
+        vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
+                              lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats)
+        E = -vals                                               # diag_tools.py:265,273
+    elif alg == "exact":
+        E, vecs = _eigs_exact(plan, n, nS, ctx)
+    elif alg == "arnoldi":
+        E, vecs = _eigs_arnoldi(plan, n, nS, guesses[0], ctx)
+    else:
+        raise ValueError("alg must be 'davidson', 'exact' or 'arnoldi'")
+    if not isinstance(orthonormalize, bool):                    # diag_tools.py:275-283
+        orthonormalize = (nS > 1) and (abs(E[0] - E[1]) < orthonormalize)
+    if nS > 1 and orthonormalize:
+        vecs = _orth(vecs, ctx)
+    N = len(mpsL[0])
+    if (site == 0 or site == N - 1) and edgePreserveState:
+        preserveState = True
+    if oneSite or alg != "exact":                               # diag_tools.py:208-211
+        E, vecs, ovlp = check_overlap(guesses[0], list(vecs), E, preserveState, ctx)
+    else:
+        ovlp = None
+    E = np.asarray(E)
+    Eout = E[0] if (nStates == 1 and E.ndim == 1) else E
+    V = torch.stack(list(vecs), dim=1)
+    if own_plan:
+        plan.close()
+    return Eout, (V if dev_in else V.cpu().numpy()), ovlp
+
+
+def _eigs_exact(plan, n, k, ctx):
+    """calc_eigs_exact: dense H (built column by column with the device mat-vec, which is
+    what diag_tools.py:30-63 contracts explicitly) + LAPACK geev on the host (:197)."""
+    if n > 4096:
+        raise ValueError("alg='exact' is a validation path for small local problems (n <= 4096)")
+    eye = torch.eye(n, dtype=ctx.tdtype, device=ctx.device)
+    H = torch.empty((n, n), dtype=ctx.tdtype, device=ctx.device)
+    for c in range(n):
+        plan.apply(eye[c], H[c], 1.0)                           # row c of H^T
+    Hh = H.cpu().numpy().T
+    vals, vv = sla.eig(Hh)
+    order = np.argsort(vals)[::-1][:k]                          # :198-200 (descending)
+    E = vals[order]
+    vecs = [ctx.dev(np.ascontiguousarray(vv[:, o]) if ctx.code == D.C128 else np.real(vv[:, o] * np.exp(-1j * np.angle(vv[np.argmax(np.abs(vv[:, o])), o]))))
+            for o in order]
+    return E, vecs
+
+
+def _eigs_arnoldi(plan, n, k, guess, ctx):
+    """calc_eigs_arnoldi (:214-241): ARPACK on the host driving the device mat-vec."""
+    from scipy.sparse.linalg import LinearOperator, eigs as arnoldi
+    xd = torch.empty(n, dtype=ctx.tdtype, device=ctx.device)
+    yd = torch.empty_like(xd)
+
+    def mv(x):
+        xd.copy_(ctx.dev(np.asarray(x).reshape(-1)))
+        plan.apply(xd, yd, -1.0)
+        return yd.cpu().numpy()
+
+    k = min(k, n - 2)
+    op = LinearOperator((n, n), matvec=mv, dtype=np.complex128)
+    try:
+        vals, vv = arnoldi(op, k=k, which="SR", v0=guess.cpu().numpy().astype(np.complex128), tol=1e-5)
+    except Exception as exc:                                    # :227-231
+        vals, vv = exc.eigenvalues, exc.eigenvectors
+    order = np.argsort(vals)[:k]
+    E = -vals[order]
+    if ctx.code == D.F64:
+        vv = np.real(vv * np.exp(-1j * np.angle(vv[np.argmax(np.abs(vv), axis=0), np.arange(vv.shape[1])])))
+    return E, [ctx.dev(np.ascontiguousarray(vv[:, o])) for o in order]
+
+
+def _orth(vecs, ctx):
+    """Orthonormal basis of span(vecs) (sla.orth, diag_tools.py:285) by device Gram-Schmidt."""
+    from .davidson import _orthonormalise
+    n = vecs[0].numel()
+    ops = D.VecOps(ctx.code, n, ctx.device)
+    tmp = torch.zeros(8, dtype=ctx.tdtype, device=ctx.device)
+    nrm = torch.zeros(1, dtype=torch.float64, device=ctx.device)
+    out = [v.clone() for v in vecs]
+    return _orthonormalise(ops, out, out, nrm, tmp)
