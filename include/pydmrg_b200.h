@@ -83,6 +83,12 @@ size_t pdmrg_heff_workspace_bytes(const pdmrg_heff_plan* plan);
 int pdmrg_heff_apply(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs,
                      const void* x, void* y, double sign, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* Same as pdmrg_heff_apply, but records CUDA events on `stream` around the three stages and
+ * SYNCHRONISES: ms3_host[0..2] = milliseconds spent in stage A (GEMM), the W mix, stage C (GEMM),
+ * summed over MPO terms.  Measurement aid for bench.py's roofline object. */
+int pdmrg_heff_apply_timed(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs,
+                           const void* x, void* y, double sign, void* workspace, size_t workspace_bytes,
+                           void* stream, float* ms3_host);
 /* MPO-bond-sharded variant: this rank applies only the (j,o) blocks whose
  * flag in block_mask_host[m][j*wR+o] is non-zero; y holds the PARTIAL sum (caller
  * all-reduces).  The mask is fixed at plan creation. */
@@ -92,6 +98,8 @@ int pdmrg_heff_plan_create_sharded(pdmrg_heff_plan** plan, int dtype, int P, int
 /* algorithmic FLOPs of one apply (dense-W count of SURVEY 8d) and with block sparsity */
 double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan);
 double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan);
+/* FLOPs the two GEMM stages of one apply actually execute (chi^3 terms of the non-empty slabs) */
+double pdmrg_heff_flops_gemm(const pdmrg_heff_plan* plan);
 
 /* ---- environment (block) updates  (E1: tools/env_tools.py:40-50, E2: :28-38) --------------
  * right-growing:  out[k,m,q] = sum L[j,l,p] Abra[i,j,k] W[l,m,i,n] A[n,p,q]
@@ -132,8 +140,11 @@ size_t pdmrg_vec_scratch_bytes(int m);
 /* ---- truncation ---------------------------------------------------------------------------
  * T2 (tools/mps_tools.py:98-120): thin SVD of a row-major (rows x cols) matrix a:
  *   a = U diag(S) Vh,  U (rows x k) row-major, S (k) descending, Vh (k x cols) row-major,
- *   k = min(rows, cols).  `a` is destroyed.  method: 0 = QR-iteration (gesvd), 1 = Jacobi
- *   (gesvdj).  info_dev: one int (device).  cuSOLVER is loaded on first use. */
+ *   k = min(rows, cols).  `a` is destroyed (methods 0, 1).  method: 0 = QR-iteration (gesvd),
+ *   1 = Jacobi (gesvdj), 2 = Gram matrix (DMMA GEMM) + heevd + Householder QR: both factors are
+ *   exact isometries, S absolute accuracy ~eps*S_0, reconstruction error O(eps*S_0^2/S_i) along
+ *   singular direction i (see csrc/solver.cu); ~7x faster at 2048^2.  info_dev: one int
+ *   (device).  cuSOLVER is loaded on first use. */
 size_t pdmrg_svd_workspace_bytes(int dtype, int rows, int cols, int method);
 int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* Vh,
               int method, void* workspace, size_t workspace_bytes, int* info_dev, void* stream);

@@ -41,8 +41,10 @@ def _load():
         "pdmrg_heff_plan_destroy": (None, [vp]),
         "pdmrg_heff_workspace_bytes": (sz, [vp]),
         "pdmrg_heff_apply": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp]),
+        "pdmrg_heff_apply_timed": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp, POINTER(ctypes.c_float)]),
         "pdmrg_heff_flops_dense": (d, [vp]),
         "pdmrg_heff_flops_sparse": (d, [vp]),
+        "pdmrg_heff_flops_gemm": (d, [vp]),
         "pdmrg_env_workspace_bytes": (sz, [i, i, i, i, i, i]),
         "pdmrg_env_update_right": (i, [i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
         "pdmrg_env_update_left": (i, [i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -23,7 +23,7 @@ struct pdmrg_heff_plan {
   std::vector<MixOpDev> mix;                         // per MPO term
   std::vector<std::vector<int>> need_o, need_j;      // per MPO term: flags
   void* dev_blob = nullptr;
-  double flops_dense = 0, flops_sparse = 0;
+  double flops_dense = 0, flops_sparse = 0, flops_gemm = 0;
   size_t ws_bytes = 0;
 };
 
@@ -95,6 +95,7 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
     const double cube_a = (double)Dr * Dr * Dl, cube_c = (double)Dl * Dl * Dr;
     pl->flops_dense += cmac * (P * (wr * cube_a + wl * cube_c) + (double)rows * cols * Dl * Dr);
     pl->flops_sparse += cmac * (P * (no * cube_a + nj * cube_c) + (double)nnz * Dl * Dr);
+    pl->flops_gemm += cmac * P * (no * cube_a + nj * cube_c);
     const size_t t_elems = (size_t)Dr * wr * P * Dl, u_elems = (size_t)P * Dr * wl * Dl;
     const size_t need = align_up(t_elems * 8 * E, 256) + align_up(u_elems * 8 * E, 256);
     if (need > pl->ws_bytes) pl->ws_bytes = need;
@@ -136,10 +137,55 @@ extern "C" void pdmrg_heff_plan_destroy(pdmrg_heff_plan* plan) {
 extern "C" size_t pdmrg_heff_workspace_bytes(const pdmrg_heff_plan* plan) { return plan ? plan->ws_bytes : 0; }
 extern "C" double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan) { return plan ? plan->flops_dense : 0; }
 extern "C" double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan) { return plan ? plan->flops_sparse : 0; }
+extern "C" double pdmrg_heff_flops_gemm(const pdmrg_heff_plan* plan) { return plan ? plan->flops_gemm : 0; }
+
+namespace {
+struct StageTimer {
+  cudaEvent_t ev[4];
+  float ms[3] = {0, 0, 0};
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  int mark(int i) {
+    if (!on) return 0;
+    PDMRG_CHECK_CUDA(cudaEventRecord(ev[i], stream));
+    return 0;
+  }
+  int collect() {
+    if (!on) return 0;
+    PDMRG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
+    for (int i = 0; i < 3; ++i) {
+      float t = 0;
+      PDMRG_CHECK_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      ms[i] += t;
+    }
+    return 0;
+  }
+};
+int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x, void* y,
+                    double sign, void* workspace, size_t workspace_bytes, cudaStream_t stream, StageTimer* tm);
+}  // namespace
 
 extern "C" int pdmrg_heff_apply(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x,
                                 void* y, double sign, void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return heff_apply_impl(pl, Ls, Rs, x, y, sign, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_), nullptr);
+}
+
+extern "C" int pdmrg_heff_apply_timed(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x,
+                                      void* y, double sign, void* workspace, size_t workspace_bytes, void* stream_,
+                                      float* ms3_host) {
+  StageTimer tm;
+  tm.on = true;
+  tm.stream = static_cast<cudaStream_t>(stream_);
+  for (int i = 0; i < 4; ++i) PDMRG_CHECK_CUDA(cudaEventCreate(&tm.ev[i]));
+  int rc = heff_apply_impl(pl, Ls, Rs, x, y, sign, workspace, workspace_bytes, tm.stream, &tm);
+  for (int i = 0; i < 3; ++i) ms3_host[i] = tm.ms[i];
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
+  return rc;
+}
+
+namespace {
+int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x, void* y,
+                    double sign, void* workspace, size_t workspace_bytes, cudaStream_t stream, StageTimer* tm) {
   PDMRG_REQUIRE(pl != nullptr, "pdmrg_heff_apply: null plan");
   PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply: workspace too small");
   const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
@@ -153,6 +199,7 @@ extern "C" int pdmrg_heff_apply(pdmrg_heff_plan* pl, const void* const* Ls, cons
     const double* R = static_cast<const double*>(Rs[m]);
     const double* L = static_cast<const double*>(Ls[m]);
     // ---- stage A: batched over runs of needed o
+    if (tm && tm->mark(0)) return 1;
     bool any = false;
     for (int o = 0; o < wr;) {
       if (!pl->need_o[m][o]) { ++o; continue; }
@@ -169,7 +216,9 @@ extern "C" int pdmrg_heff_apply(pdmrg_heff_plan* pl, const void* const* Ls, cons
     }
     if (!any) continue;
     // ---- mix
+    if (tm && tm->mark(1)) return 1;
     if (launch_mix(pl->dtype, pl->mix[m], T, U, Dr, Dl, (long long)wr * P * Dl, 1, (long long)wl * Dl, 1, stream)) return 1;
+    if (tm && tm->mark(2)) return 1;
     // ---- stage C: contiguous runs of needed j, accumulated into y
     for (int j = 0; j < wl;) {
       if (!pl->need_j[m][j]) { ++j; continue; }
@@ -183,10 +232,12 @@ extern "C" int pdmrg_heff_apply(pdmrg_heff_plan* pl, const void* const* Ls, cons
       wrote_y = true;
       j = j1;
     }
+    if (tm && (tm->mark(3) || tm->collect())) return 1;
   }
   if (!wrote_y) PDMRG_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)P * Dl * Dr * 8 * E, stream));
   return 0;
 }
+}  // namespace
 
 // ---------------------------------------------------------------------------------------
 // Environment updates

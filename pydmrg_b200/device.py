@@ -144,6 +144,7 @@ class HeffPlan:
         self.workspace = workspace
         self.flops_dense = float(lib.pdmrg_heff_flops_dense(self._plan))
         self.flops_sparse = float(lib.pdmrg_heff_flops_sparse(self._plan))
+        self.flops_gemm = float(lib.pdmrg_heff_flops_gemm(self._plan))
         self.n_apply = 0
 
     def apply(self, x, y, sign=-1.0):
@@ -153,6 +154,14 @@ class HeffPlan:
                                    ws.numel(), _stream()), "pdmrg_heff_apply")
         self.n_apply += 1
         return y
+
+    def apply_timed(self, x, y, sign=-1.0):
+        """apply() with per-stage CUDA-event timing; returns [ms stage A, ms mix, ms stage C]."""
+        ws = self.workspace.get(self.ws_bytes)
+        ms = (ctypes.c_float * 3)()
+        check(lib.pdmrg_heff_apply_timed(self._plan, self._Lp, self._Rp, _ptr(x), _ptr(y), float(sign), _ptr(ws),
+                                         ws.numel(), _stream(), ms), "pdmrg_heff_apply_timed")
+        return [float(v) for v in ms]
 
     def close(self):
         if self._plan:
@@ -262,6 +271,7 @@ class VecOps:
 # ------------------------------------------------------------------------------------------
 SVD_GESVD = 0
 SVD_GESVDJ = 1
+SVD_GRAM = 2
 
 
 def svd(a, workspace, method=SVD_GESVD):

@@ -35,7 +35,7 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     m = ctx.empty(rows, cols)
     # m[(k,n),(q,s)] = psi[n,q,k,s]      (mps_tools.py:105-107)
     D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
-    U, S, Vh, info = D.svd(m, ctx.svd_ws, ctx.svd_method)
+    U, S, Vh, info = D.svd(m, ctx.svd_ws, ctx.svd_method_for(rows, cols))
     kfull = min(rows, cols)
     Sh = S.cpu().numpy()                                        # sync; also validates the factorisation
     if int(info.item()) != 0:
@@ -172,6 +172,6 @@ def rdm_renormalize_left(psis, shape, prvs, ctx, n_avg=None):
 def _entropy_of(Mmat, ctx):
     """Entanglement of one state from its own singular values (dmrg.py:30-47)."""
     a = Mmat.clone()
-    _, S, _, info = D.svd(a, ctx.svd_ws, ctx.svd_method)
+    _, S, _, info = D.svd(a, ctx.svd_ws, ctx.svd_method_for(*a.shape))
     EE, EEs, _ = calc_entanglement(S.cpu().numpy())
     return EE, EEs

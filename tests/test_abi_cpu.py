@@ -1,0 +1,99 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports every symbol declared in
+include/pydmrg_b200.h; host-side logic of the package (MPS utilities, MPO combination)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = os.path.join(ROOT, "pydmrg_b200", "libpydmrg_b200.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as g
+        g.build()
+    from pydmrg_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "pydmrg_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pdmrg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib.lib, name), name
+    assert set(lib.EXPORTS) == set(declared)
+    assert lib.lib.pdmrg_version() >= 100
+    assert lib.lib.pdmrg_launch_count() == 0        # nothing ran: no compute without a GPU
+
+
+def test_argument_validation_without_gpu(lib):
+    """Error behaviour: bad arguments are rejected on the host with a message (no launch)."""
+    rc = lib.lib.pdmrg_gemm_nt(7, 4, 4, 4, 1, None, 4, 0, None, 4, 0, 0, None, 4, 0, 1.0, 0.0, 0, None)
+    assert rc != 0 and b"dtype" in lib.lib.pdmrg_last_error()
+    rc = lib.lib.pdmrg_gemm_nt(0, 4, 4, 4, 1, None, 4, 0, None, 4, 0, 0, None, 4, 0, 1.0, 0.0, 3, None)
+    assert rc != 0 and b"beta" in lib.lib.pdmrg_last_error()
+    with pytest.raises(lib.PdmrgError):
+        lib.check(rc, "pdmrg_gemm_nt")
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import the oracle (or the reference)."""
+    pkg = os.path.join(ROOT, "pydmrg_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|tools\.|dmrg\b|idmrg\b)", src, re.M), fn
+            assert "ref_loader" not in src and "sys.path.insert(0, '/root/reference" not in src, fn
+
+
+def test_mps_utils_match_oracle_draw_order():
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import mps as mt
+    for N in (5, 6, 9):
+        np.random.seed(4)
+        a = mt.create_rand_mps(N, 7)
+        np.random.seed(4)
+        b = orc.random_mps(N, 7)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        a = mt.make_mps_right(a); b = orc.make_mps_right(b)
+        assert all(np.allclose(x, y) for x, y in zip(a, b))
+        for t in a[1:]:
+            assert np.allclose(np.einsum("ijk,ilk->jl", t, t.conj()), np.eye(t.shape[1]), atol=1e-12)
+
+
+def test_increase_mbd_and_io(tmp_path):
+    from pydmrg_b200 import mps as mt
+    np.random.seed(1)
+    mpsL = mt.create_all_mps(7, 4, 2)
+    big = mt.increase_all_mbd([[t.copy() for t in M] for M in mpsL], 16)
+    dims = [t.shape for t in big[0]]
+    assert dims[0] == (2, 1, 2) and dims[3] == (2, 8, 8) and dims[-1] == (2, 2, 1)
+    assert np.allclose(big[0][3][:, :4, :4], mpsL[0][3])
+    fn = str(tmp_path / "state")
+    mt.save_mps(big, fn, gaugeSite=3, fformat="npz")
+    back, site = mt.load_mps(fn, fformat="npz")
+    assert int(site) == 3 and len(back) == 2
+    assert all(np.array_equal(x, y) for x, y in zip(back[1], big[1]))
+
+
+def test_combined_operator_matches_oracle_dense():
+    """Wc built on the host is exactly the operator the oracle contracts."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import mpo as M
+    # device.combine_* are pure NumPy helpers; import without touching CUDA
+    from pydmrg_b200.device import combine_onesite, combine_twosite
+    W1, W2 = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))[0][2:4]
+    rng = np.random.default_rng(0)
+    Dl, Dr, w, d = 3, 2, 6, 2
+    L = rng.standard_normal((Dl, w, Dl)); R = rng.standard_normal((Dr, w, Dr))
+    Wc = combine_twosite(W1, W2, np.float64).reshape(w, d * d, w, d * d)
+    H = np.einsum("ijk,jaob,ros->airbks", L, Wc, R).reshape(d * d * Dl * Dr, -1)
+    Hd = orc.heff_dense_twosite([L], [W1], [W2], [R], (d, d, Dl, Dr))
+    assert np.allclose(H, Hd)
+    Wc1 = combine_onesite(W1, w, w, d, np.float64).reshape(w, d, w, d)
+    H1 = np.einsum("pnm,nojl,ijk->opilmk", L, Wc1, R).reshape(d * Dl * Dr, -1)
+    assert np.allclose(H1, orc.heff_dense_onesite([L], [W1], [R], (d, Dl, Dr)))
