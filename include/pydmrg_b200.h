@@ -56,6 +56,17 @@ int pdmrg_gemm_nt(int dtype, int M, int N, int K, int batch,
                   void* C, long long ldc, long long strideC,
                   double alpha_re, double alpha_im, int beta, void* stream);
 
+/* Same product with TWO batch levels, b = (b1, b2): the operand / result offsets are
+ * b1*stride?1 + idx2[b2]*stride?2 (idx2_host = NULL means idx2[b2] = b2; nb2 <= 32).  The index
+ * list lets one launch visit only the non-empty MPO-bond slabs. */
+int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                           const void* A, long long lda, long long strideA1, long long strideA2,
+                           const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                           void* C, long long ldc, long long strideC1, long long strideC2,
+                           double alpha_re, double alpha_im, int beta, void* stream);
+/* force the 128- or 64-row CTA tile (0 = automatic wave-quantisation model); testing only */
+void pdmrg_set_force_tile_rows(int bm);
+
 /* ---- strided 4-index copy:  out[i0,i1,i2,i3] (C-order, dims n0..n3) = f(in[sum i_k*s_k])
  * f = conj if conj != 0; if scale != NULL the element is multiplied by the REAL vector
  * scale[i_{scale_axis}] (device pointer).  Strides in elements. */

@@ -35,6 +35,8 @@ def _load():
         "pdmrg_last_gemm_path": (i, []),
         "pdmrg_set_force_generic_gemm": (None, [i]),
         "pdmrg_gemm_nt": (i, [i, i, i, i, i, vp, ll, ll, vp, ll, ll, i, vp, ll, ll, d, d, i, vp]),
+        "pdmrg_gemm_nt_batched2": (i, [i, i, i, i, i, i, POINTER(i), vp, ll, ll, ll, vp, ll, ll, ll, i, vp, ll, ll, ll, d, d, i, vp]),
+        "pdmrg_set_force_tile_rows": (None, [i]),
         "pdmrg_permute4": (i, [i, vp, vp, i, i, i, i, ll, ll, ll, ll, i, vp, i, vp]),
         "pdmrg_heff_plan_create": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp)]),
         "pdmrg_heff_plan_create_sharded": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp)]),

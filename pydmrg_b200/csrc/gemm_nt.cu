@@ -24,23 +24,29 @@
 namespace pdmrg {
 namespace {
 
-constexpr int BM = 128;          // rows of A per CTA tile
+constexpr int BM_MAX = 128;      // rows of A per CTA tile: 128 (8 m-tiles per warp) or 64 (4)
 constexpr int BNR = 128;         // REAL columns of C per CTA tile (64 complex columns)
 constexpr int BK = 16;           // doubles per k-iteration (= one 128-byte swizzle row)
 constexpr int STAGES = 6;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int A_BYTES = BM * BK * 8;           // 16 KiB
+constexpr int A_BYTES = BM_MAX * BK * 8;       // 16 KiB (the 64-row variant uses the first half)
 constexpr int STAGE_BYTES = 2 * A_BYTES;       // B tile lives at +A_BYTES (8 or 16 KiB used)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 
+constexpr int MAX_IDX2 = 32;
+
+// Two batch levels: b = b1 * nb2 + b2; the second level may be an index list (idx2[b2]) so that
+// e.g. only the non-empty MPO-bond slabs are visited, in ONE launch (no per-slab wave tails).
 struct GemmParams {
   int M, N;                 // N = columns of C in ELEMENTS (complex columns when CPLX)
-  int kiters, batch, tiles_m, tiles_n;
-  long long ldc, strideC;   // elements
+  int kiters, nb1, nb2, tiles_m, tiles_n;
+  long long ldc, strideC1, strideC2;   // elements
   double* C;
   double alpha_re, alpha_im;
-  int beta, conjB, bcastA, bcastB;
+  int beta, conjB;
+  int bcastA1, bcastA2, bcastB1, bcastB2;
+  int idx2[MAX_IDX2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -67,11 +73,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -80,7 +86,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <bool CPLX>
+template <bool CPLX, int MI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -103,9 +109,10 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   __syncthreads();
 
-  const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
+  constexpr int BM = 16 * MI;                       // 128 or 64 rows per CTA tile
+  const int total_tiles = p.tiles_m * p.tiles_n * p.nb1 * p.nb2;
   constexpr int B_ROWS = CPLX ? BNR / 2 : BNR;
-  constexpr uint32_t TX_BYTES = A_BYTES + B_ROWS * BK * 8;
+  constexpr uint32_t TX_BYTES = BM * BK * 8 + B_ROWS * BK * 8;
 
   if (warp == CONSUMER_WARPS) {
     // ------------------------------ TMA producer ------------------------------------
@@ -118,14 +125,16 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tn = rest % p.tiles_n;
         const int b = rest / p.tiles_n;
         const int rowA = tm * BM, rowB = tn * B_ROWS;
-        const int bA = p.bcastA ? 0 : b, bB = p.bcastB ? 0 : b;
+        const int b1 = b / p.nb2, b2 = p.idx2[b % p.nb2];
+        const int a1 = p.bcastA1 ? 0 : b1, a2 = p.bcastA2 ? 0 : b2;
+        const int c1 = p.bcastB1 ? 0 : b1, c2 = p.bcastB2 ? 0 : b2;
         for (int kit = 0; kit < p.kiters; ++kit) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t full = full0 + 8 * stage;
           mbar_expect_tx(full, TX_BYTES);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
-          tma_load_3d(sA, &tmA, kit * BK, rowA, bA, full);
-          tma_load_3d(sA + A_BYTES, &tmB, kit * BK, rowB, bB, full);
+          tma_load_4d(sA, &tmA, kit * BK, rowA, a2, a1, full);
+          tma_load_4d(sA + A_BYTES, &tmB, kit * BK, rowB, c2, c1, full);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -140,7 +149,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // 64-bit shared load then touch rows {0,2,4,6} / {1,3,5,7}, which the 128B swizzle
   // spreads over all banks (conflict-free).
   const int permg = ((g & 3) << 1) | (g >> 2);
-  const uint32_t offA = (wm * 64 + permg) * 128 + ((t & 1) << 3) + ((((t >> 1) ^ permg) & 7) << 4);
+  const uint32_t offA = (wm * (8 * MI) + permg) * 128 + ((t & 1) << 3) + ((((t >> 1) ^ permg) & 7) << 4);
   uint32_t offB;
   uint32_t signmask = 0;
   if (CPLX) {
@@ -160,9 +169,9 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int tn = rest % p.tiles_n;
     const int b = rest / p.tiles_n;
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
@@ -172,9 +181,9 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const unsigned char* sB = sA + A_BYTES;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        double a[8], bf[4];
+        double a[MI], bf[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
           a[i] = *reinterpret_cast<const double*>(sA + (offA ^ (kk << 5)) + i * 1024);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -187,7 +196,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
       }
@@ -197,12 +206,12 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     // ------------------------------ epilogue ----------------------------------------
-    double* Cb = p.C + (CPLX ? 2 : 1) * (long long)b * p.strideC;
-    const int row0 = tm * BM + wm * 64 + permg;
+    double* Cb = p.C + (CPLX ? 2 : 1) * ((long long)(b / p.nb2) * p.strideC1 + (long long)p.idx2[b % p.nb2] * p.strideC2);
+    const int row0 = tm * BM + wm * (8 * MI) + permg;
     if (CPLX) {
       const int col0 = tn * (BNR / 2) + wn * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MI; ++i) {
         const int row = row0 + i * 8;
         if (row >= p.M) continue;
 #pragma unroll
@@ -221,7 +230,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int g0 = 2 * t, g1 = 2 * t + 1;
       const int pc0 = ((g0 & 3) << 1) | (g0 >> 2), pc1 = ((g1 & 3) << 1) | (g1 >> 2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MI; ++i) {
         const int row = row0 + i * 8;
         if (row >= p.M) continue;
 #pragma unroll
@@ -249,17 +258,17 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
-gemm_nt_generic_kernel(int M, int N, int K, const double* __restrict__ A, long long lda, long long strideA,
-                       const double* __restrict__ B, long long ldb, long long strideB, int conjB,
-                       double* __restrict__ C, long long ldc, long long strideC,
-                       double alpha_re, double alpha_im, int beta) {
+gemm_nt_generic_kernel(int M, int N, int K, const double* __restrict__ A, long long lda, long long strideA1, long long strideA2,
+                       const double* __restrict__ B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                       double* __restrict__ C, long long ldc, long long strideC1, long long strideC2,
+                       double alpha_re, double alpha_im, int beta, int nb2, GemmParams idx) {
   constexpr int E = CPLX ? 2 : 1;
   __shared__ double sA[32][16 * E + 1];
   __shared__ double sB[32][16 * E + 1];
-  const int b = blockIdx.z;
-  const double* Ab = A + E * (long long)b * strideA;
-  const double* Bb = B + E * (long long)b * strideB;
-  double* Cb = C + E * (long long)b * strideC;
+  const long long b1 = blockIdx.z / nb2, b2 = idx.idx2[blockIdx.z % nb2];
+  const double* Ab = A + E * (b1 * strideA1 + b2 * strideA2);
+  const double* Bb = B + E * (b1 * strideB1 + b2 * strideB2);
+  double* Cb = C + E * (b1 * strideC1 + b2 * strideC2);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
@@ -324,17 +333,20 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 3-D map over a row-major matrix viewed as REAL doubles: dims {kreal, rows, batch}
+// 4-D map over a row-major matrix viewed as REAL doubles: dims {kreal, rows, n2, n1}
 int make_map(CUtensorMap* tm, const void* base, long long kreal, long long rows, long long ld_real,
-             long long batch, long long stride_real, int box_rows) {
+             long long n2, long long stride2_real, long long n1, long long stride1_real, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
-  cuuint64_t dims[3] = {(cuuint64_t)kreal, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld_real * 8,
-                           (cuuint64_t)((batch > 1 && stride_real > 0) ? stride_real : rows * ld_real) * 8};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+  if (n2 < 1) n2 = 1;
+  if (n1 < 1) n1 = 1;
+  const long long dflt = rows * ld_real;          // any valid (16-byte multiple) stride for extent-1 dims
+  cuuint64_t dims[4] = {(cuuint64_t)kreal, (cuuint64_t)rows, (cuuint64_t)n2, (cuuint64_t)n1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld_real * 8, (cuuint64_t)((n2 > 1 && stride2_real > 0) ? stride2_real : dflt) * 8,
+                           (cuuint64_t)((n1 > 1 && stride1_real > 0) ? stride1_real : dflt) * 8};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return 1; }
@@ -343,6 +355,18 @@ int make_map(CUtensorMap* tm, const void* base, long long kreal, long long rows,
 
 std::atomic<int> g_last_path{0};
 std::atomic<int> g_force_generic{0};
+std::atomic<int> g_force_bm{0};
+
+// wave-quantisation cost model: time ~ waves * tile height; the 64-row tile pays a small
+// efficiency penalty (more B traffic per FLOP) but halves the tail of a partial wave
+int choose_bm(long long M, long long tiles_n, long long nbatch) {
+  if (g_force_bm.load() == 64 || g_force_bm.load() == 128) return g_force_bm.load();
+  const long long sms = num_sms();
+  const long long t128 = ((M + 127) / 128) * tiles_n * nbatch, t64 = ((M + 63) / 64) * tiles_n * nbatch;
+  const double c128 = (double)((t128 + sms - 1) / sms) * 1.0;
+  const double c64 = (double)((t64 + sms - 1) / sms) * 0.5 * 1.04;
+  return c64 < c128 ? 64 : 128;
+}
 
 }  // namespace
 }  // namespace pdmrg
@@ -351,72 +375,104 @@ using namespace pdmrg;
 
 extern "C" int pdmrg_last_gemm_path(void) { return g_last_path.load(); }
 extern "C" void pdmrg_set_force_generic_gemm(int on) { g_force_generic.store(on); }
+extern "C" void pdmrg_set_force_tile_rows(int bm) { g_force_bm.store(bm); }
 
-extern "C" int pdmrg_gemm_nt(int dtype, int M, int N, int K, int batch, const void* A, long long lda,
-                             long long strideA, const void* B, long long ldb, long long strideB, int conjB,
-                             void* C, long long ldc, long long strideC, double alpha_re, double alpha_im,
-                             int beta, void* stream_) {
+extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                                      const void* A, long long lda, long long strideA1, long long strideA2,
+                                      const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                                      void* C, long long ldc, long long strideC1, long long strideC2,
+                                      double alpha_re, double alpha_im, int beta, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_gemm_nt: bad dtype");
   PDMRG_REQUIRE(beta == 0 || beta == 1, "pdmrg_gemm_nt: beta must be 0 or 1");
-  PDMRG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "pdmrg_gemm_nt: negative extent");
-  if (M == 0 || N == 0 || batch == 0) return 0;
+  PDMRG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && nb1 >= 0 && nb2 >= 0, "pdmrg_gemm_nt: negative extent");
+  PDMRG_REQUIRE(nb2 <= MAX_IDX2, "pdmrg_gemm_nt: second batch level limited to 32 entries");
+  if (M == 0 || N == 0 || nb1 == 0 || nb2 == 0) return 0;
   const bool cplx = dtype == PDMRG_C128;
   if (!cplx) { PDMRG_REQUIRE(alpha_im == 0.0, "pdmrg_gemm_nt: complex alpha with real dtype"); }
   const int E = cplx ? 2 : 1;
 
-  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool strides_ok = ((lda * E) % 2 == 0) && ((ldb * E) % 2 == 0) && ((strideA * E) % 2 == 0) &&
-                          ((strideB * E) % 2 == 0);
-  const double work = (double)M * N * (double)(K > 0 ? K : 1) * batch * (cplx ? 4 : 1);
+  GemmParams p;
+  int max2 = 0;
+  for (int i = 0; i < MAX_IDX2; ++i) p.idx2[i] = 0;
+  for (int i = 0; i < nb2; ++i) {
+    p.idx2[i] = idx2_host ? idx2_host[i] : i;
+    PDMRG_REQUIRE(p.idx2[i] >= 0, "pdmrg_gemm_nt: negative batch index");
+    if (p.idx2[i] > max2) max2 = p.idx2[i];
+  }
+  const long long nbatch = (long long)nb1 * nb2;
+
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  auto even = [&](long long v) { return (v * E) % 2 == 0; };
+  const bool strides_ok = even(lda) && even(ldb) && even(strideA1) && even(strideA2) && even(strideB1) && even(strideB2);
+  const double work = (double)M * N * (double)(K > 0 ? K : 1) * (double)nbatch * (cplx ? 4 : 1);
   const bool use_tma = !g_force_generic.load() && K > 0 && aligned16(A) && aligned16(B) && strides_ok &&
                        (!cplx || aligned16(C)) && work >= 64.0 * 64.0 * 64.0;
+
+  p.M = M; p.N = N;
+  p.nb1 = nb1; p.nb2 = nb2;
+  p.ldc = ldc; p.strideC1 = strideC1; p.strideC2 = strideC2;
+  p.C = static_cast<double*>(C);
+  p.alpha_re = alpha_re; p.alpha_im = alpha_im;
+  p.beta = beta; p.conjB = conjB;
+  p.bcastA1 = (strideA1 == 0 || nb1 == 1); p.bcastA2 = (strideA2 == 0 || max2 == 0);
+  p.bcastB1 = (strideB1 == 0 || nb1 == 1); p.bcastB2 = (strideB2 == 0 || max2 == 0);
 
   if (use_tma) {
     static bool attr_set = false;
     if (!attr_set) {
-      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set = true;
     }
-    CUtensorMap tmA, tmB;
     const long long kreal = (long long)K * E;
-    if (make_map(&tmA, A, kreal, M, lda * E, strideA == 0 ? 1 : batch, strideA * E, BM)) return 1;
-    if (make_map(&tmB, B, kreal, N, ldb * E, strideB == 0 ? 1 : batch, strideB * E, cplx ? BNR / 2 : BNR)) return 1;
-    GemmParams p;
-    p.M = M; p.N = N;
-    p.kiters = (int)((kreal + BK - 1) / BK);
-    p.batch = batch;
-    p.tiles_m = (M + BM - 1) / BM;
     const int bn = cplx ? BNR / 2 : BNR;
+    p.kiters = (int)((kreal + BK - 1) / BK);
     p.tiles_n = (N + bn - 1) / bn;
-    p.ldc = ldc; p.strideC = strideC;
-    p.C = static_cast<double*>(C);
-    p.alpha_re = alpha_re; p.alpha_im = alpha_im;
-    p.beta = beta; p.conjB = conjB;
-    p.bcastA = (strideA == 0 || batch == 1); p.bcastB = (strideB == 0 || batch == 1);
-    const long long total = (long long)p.tiles_m * p.tiles_n * batch;
+    const int bm = choose_bm(M, p.tiles_n, nbatch);
+    p.tiles_m = (M + bm - 1) / bm;
+    CUtensorMap tmA, tmB;
+    if (make_map(&tmA, A, kreal, M, lda * E, p.bcastA2 ? 1 : max2 + 1, strideA2 * E, p.bcastA1 ? 1 : nb1, strideA1 * E, bm)) return 1;
+    if (make_map(&tmB, B, kreal, N, ldb * E, p.bcastB2 ? 1 : max2 + 1, strideB2 * E, p.bcastB1 ? 1 : nb1, strideB1 * E, bn)) return 1;
+    const long long total = (long long)p.tiles_m * p.tiles_n * nbatch;
+    PDMRG_REQUIRE(total < (1ll << 31), "pdmrg_gemm_nt: too many tiles");
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    if (cplx)
-      gemm_nt_dmma_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
-    else
-      gemm_nt_dmma_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    if (bm == 128) {
+      if (cplx) gemm_nt_dmma_kernel<true, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+      else gemm_nt_dmma_kernel<false, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    } else {
+      if (cplx) gemm_nt_dmma_kernel<true, 4><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+      else gemm_nt_dmma_kernel<false, 4><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    }
     PDMRG_CHECK_LAUNCH();
     count_launch();
     g_last_path.store(1);
     return 0;
   }
 
-  dim3 grid((N + 31) / 32, (M + 31) / 32, batch);
-  PDMRG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "pdmrg_gemm_nt: generic path extent too large");
+  dim3 grid((N + 31) / 32, (M + 31) / 32, (unsigned)nbatch);
+  PDMRG_REQUIRE(grid.y <= 65535 && nbatch <= 65535, "pdmrg_gemm_nt: generic path extent too large");
+  p.kiters = 0; p.tiles_m = p.tiles_n = 0;
   if (cplx)
-    gemm_nt_generic_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, (const double*)A, lda, strideA, (const double*)B, ldb,
-                                                           strideB, conjB, (double*)C, ldc, strideC, alpha_re, alpha_im, beta);
+    gemm_nt_generic_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, (const double*)A, lda, strideA1, strideA2, (const double*)B, ldb,
+                                                           strideB1, strideB2, conjB, (double*)C, ldc, strideC1, strideC2,
+                                                           alpha_re, alpha_im, beta, nb2, p);
   else
-    gemm_nt_generic_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, (const double*)A, lda, strideA, (const double*)B, ldb,
-                                                            strideB, 0, (double*)C, ldc, strideC, alpha_re, 0.0, beta);
+    gemm_nt_generic_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, (const double*)A, lda, strideA1, strideA2, (const double*)B, ldb,
+                                                            strideB1, strideB2, 0, (double*)C, ldc, strideC1, strideC2,
+                                                            alpha_re, 0.0, beta, nb2, p);
   PDMRG_CHECK_LAUNCH();
   count_launch();
   g_last_path.store(2);
   return 0;
+}
+
+extern "C" int pdmrg_gemm_nt(int dtype, int M, int N, int K, int batch, const void* A, long long lda,
+                             long long strideA, const void* B, long long ldb, long long strideB, int conjB,
+                             void* C, long long ldc, long long strideC, double alpha_re, double alpha_im,
+                             int beta, void* stream_) {
+  return pdmrg_gemm_nt_batched2(dtype, M, N, K, batch, 1, nullptr, A, lda, strideA, 0, B, ldb, strideB, 0, conjB, C, ldc,
+                                strideC, 0, alpha_re, alpha_im, beta, stream_);
 }

@@ -96,7 +96,7 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
     pl->flops_dense += cmac * (P * (wr * cube_a + wl * cube_c) + (double)rows * cols * Dl * Dr);
     pl->flops_sparse += cmac * (P * (no * cube_a + nj * cube_c) + (double)nnz * Dl * Dr);
     pl->flops_gemm += cmac * P * (no * cube_a + nj * cube_c);
-    const size_t t_elems = (size_t)Dr * wr * P * Dl, u_elems = (size_t)P * Dr * wl * Dl;
+    const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl, u_elems = (size_t)P * Dr * wl * Dl;   // T also hosts Z
     const size_t need = align_up(t_elems * 8 * E, 256) + align_up(u_elems * 8 * E, 256);
     if (need > pl->ws_bytes) pl->ws_bytes = need;
   }
@@ -193,45 +193,42 @@ int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* cons
   bool wrote_y = false;
   for (int m = 0; m < pl->n_mpo; ++m) {
     const int wl = pl->wL[m], wr = pl->wR[m];
-    const size_t t_elems = (size_t)Dr * wr * P * Dl;
+    const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl;
     double* T = static_cast<double*>(workspace);
     double* U = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align_up(t_elems * 8 * E, 256));
     const double* R = static_cast<const double*>(Rs[m]);
     const double* L = static_cast<const double*>(Ls[m]);
-    // ---- stage A: batched over runs of needed o
+    // ---- stage A: ONE launch, batched over the non-empty o slabs (index list)
     if (tm && tm->mark(0)) return 1;
-    bool any = false;
-    for (int o = 0; o < wr;) {
-      if (!pl->need_o[m][o]) { ++o; continue; }
-      int o1 = o;
-      while (o1 < wr && pl->need_o[m][o1]) ++o1;
-      any = true;
-      if (pdmrg_gemm_nt(pl->dtype, Dr, P * Dl, Dr, o1 - o,
-                        R + (size_t)E * o * Dr, (long long)wr * Dr, Dr,
-                        x, Dr, 0, 0,
-                        T + (size_t)E * o * P * Dl, (long long)wr * P * Dl, (long long)P * Dl,
-                        1.0, 0.0, 0, stream))
-        return 1;
-      o = o1;
-    }
-    if (!any) continue;
+    std::vector<int> olist, jlist;
+    for (int o = 0; o < wr; ++o) if (pl->need_o[m][o]) olist.push_back(o);
+    for (int j = 0; j < wl; ++j) if (pl->need_j[m][j]) jlist.push_back(j);
+    if (olist.empty() || jlist.empty()) continue;
+    PDMRG_REQUIRE(olist.size() <= 32 && jlist.size() <= 32, "pdmrg_heff_apply: MPO bond dimension above 32 not supported yet");
+    if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, P * Dl, Dr, 1, (int)olist.size(), olist.data(),
+                               R, (long long)wr * Dr, 0, Dr,
+                               x, Dr, 0, 0, 0,
+                               T, (long long)wr * P * Dl, 0, (long long)P * Dl,
+                               1.0, 0.0, 0, stream))
+      return 1;
     // ---- mix
     if (tm && tm->mark(1)) return 1;
     if (launch_mix(pl->dtype, pl->mix[m], T, U, Dr, Dl, (long long)wr * P * Dl, 1, (long long)wl * Dl, 1, stream)) return 1;
     if (tm && tm->mark(2)) return 1;
-    // ---- stage C: contiguous runs of needed j, accumulated into y
-    for (int j = 0; j < wl;) {
-      if (!pl->need_j[m][j]) { ++j; continue; }
-      int j1 = j;
-      while (j1 < wl && pl->need_j[m][j1]) ++j1;
-      if (pdmrg_gemm_nt(pl->dtype, Dl, Dr, (j1 - j) * Dl, P,
-                        L + (size_t)E * j * Dl, (long long)wl * Dl, 0,
-                        U + (size_t)E * j * Dl, (long long)wl * Dl, (long long)Dr * wl * Dl, 0,
-                        y, Dr, (long long)Dl * Dr, sign, 0.0, wrote_y ? 1 : 0, stream))
-        return 1;
-      wrote_y = true;
-      j = j1;
-    }
+    // ---- stage C: split over the MPO bond j (ONE launch, P x |j| batches, K = Dl each) into the slabs
+    //      Z[pout][j][i][r] (aliases T, which is dead after the mix), then an ordered reduction over j:
+    //      removes the partial-wave tail of the long-K formulation and fills the GPU at small chi.
+    double* Z = T;
+    if (pdmrg_gemm_nt_batched2(pl->dtype, Dl, Dr, Dl, P, (int)jlist.size(), jlist.data(),
+                               L, (long long)wl * Dl, 0, Dl,
+                               U, (long long)wl * Dl, (long long)Dr * wl * Dl, Dl, 0,
+                               Z, Dr, (long long)wl * Dl * Dr, (long long)Dl * Dr,
+                               1.0, 0.0, 0, stream))
+      return 1;
+    if (launch_reduce_slabs(pl->dtype, Z, y, (long long)Dl * Dr, P, (int)jlist.size(), jlist.data(),
+                            (long long)wl * Dl * Dr, (long long)Dl * Dr, sign, wrote_y ? 1 : 0, stream))
+      return 1;
+    wrote_y = true;
     if (tm && (tm->mark(3) || tm->collect())) return 1;
   }
   if (!wrote_y) PDMRG_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)P * Dl * Dr * 8 * E, stream));

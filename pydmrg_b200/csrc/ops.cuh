@@ -35,4 +35,8 @@ int upload_mix_op(const MixOpHost& h, void* dst, MixOpDev* dev, cudaStream_t str
 int launch_mix(int dtype, const MixOpDev& op, const void* in, void* out, int nx, int ny,
                long long six, long long siy, long long sox, long long soy, cudaStream_t stream);
 
+// y[b,:] = sign * sum_q Z[b, idx[q], :] (+ y): ordered (deterministic) reduction of split-K slabs
+int launch_reduce_slabs(int dtype, const void* Z, void* y, long long n_elems, int nb, int nq, const int* idx_host,
+                        long long zstride_b, long long zstride_q, double sign, int accumulate, cudaStream_t stream);
+
 }  // namespace pdmrg

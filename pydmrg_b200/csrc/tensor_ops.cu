@@ -62,6 +62,23 @@ mix_kernel(MixOpDev op, const double* __restrict__ in, double* __restrict__ out,
   }
 }
 
+// y[b, e] = sign * sum_{q < nq} Z[b, idx[q], e]  (+ y[b, e] if accumulate); doubles (complex = 2 per element)
+struct SlabIdx { int v[32]; };
+__global__ void __launch_bounds__(256)
+reduce_slabs_kernel(const double* __restrict__ Z, double* __restrict__ y, long long nd, int nb, int nq, SlabIdx idx,
+                    long long zstride_b, long long zstride_q, double sign, int accumulate) {
+  const long long total = nd * nb;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / nd, e = t - b * nd;
+    const double* z = Z + b * zstride_b + e;
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q) acc += z[idx.v[q] * zstride_q];
+    acc *= sign;
+    if (accumulate) acc += y[t];
+    y[t] = acc;
+  }
+}
+
 int grid_for(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 8;
@@ -95,6 +112,21 @@ int upload_mix_op(const MixOpHost& h, void* dst, MixOpDev* dev, cudaStream_t str
   dev->val = reinterpret_cast<const double*>(d + o2);
   dev->out_off = reinterpret_cast<const long long*>(d + o3);
   dev->rows = h.rows();
+  return 0;
+}
+
+int launch_reduce_slabs(int dtype, const void* Z, void* y, long long n_elems, int nb, int nq, const int* idx_host,
+                        long long zstride_b, long long zstride_q, double sign, int accumulate, cudaStream_t stream) {
+  if (n_elems == 0 || nb == 0) return 0;
+  PDMRG_REQUIRE(nq <= 32, "reduce_slabs: more than 32 slabs");
+  const int E = dtype == PDMRG_C128 ? 2 : 1;
+  SlabIdx idx;
+  for (int q = 0; q < 32; ++q) idx.v[q] = q < nq ? idx_host[q] : 0;
+  const long long nd = n_elems * E;
+  const int grid = grid_for(nd * nb, 256);
+  reduce_slabs_kernel<<<grid, 256, 0, stream>>>((const double*)Z, (double*)y, nd, nb, nq, idx, zstride_b * E, zstride_q * E, sign, accumulate);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
   return 0;
 }
 
