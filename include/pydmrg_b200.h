@@ -152,13 +152,18 @@ size_t pdmrg_vec_scratch_bytes(int m);
  * T2 (tools/mps_tools.py:98-120): thin SVD of a row-major (rows x cols) matrix a:
  *   a = U diag(S) Vh,  U (rows x k) row-major, S (k) descending, Vh (k x cols) row-major,
  *   k = min(rows, cols).  `a` is destroyed (methods 0, 1).  method: 0 = QR-iteration (gesvd),
- *   1 = Jacobi (gesvdj), 2 = Gram matrix (DMMA GEMM) + heevd + Householder QR: both factors are
- *   exact isometries, S absolute accuracy ~eps*S_0, reconstruction error O(eps*S_0^2/S_i) along
- *   singular direction i (see csrc/solver.cu); ~7x faster at 2048^2.  info_dev: one int
+ *   1 = Jacobi (gesvdj), 2 = Gram matrix (DMMA GEMM) + heevd + Householder QR with up to two tail
+ *   refinement levels: both factors are exact isometries, reconstruction error ~1e-12*S_0 (see
+ *   csrc/solver.cu); 5-8x faster at 2048^2; this method SYNCHRONISES the stream.  info_dev: one int
  *   (device).  cuSOLVER is loaded on first use. */
 size_t pdmrg_svd_workspace_bytes(int dtype, int rows, int cols, int method);
 int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* Vh,
               int method, void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
+/* Same, when the caller will only use the `keep` leading singular triplets (chi truncation):
+ * U (rows x k), S (k), Vh (k x cols) keep their full-size layout but only columns / entries /
+ * rows [0, keep) are defined for method 2 (S[keep:] = 0); methods 0 and 1 compute everything. */
+int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, void* U, double* S, void* Vh,
+                   int method, void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
 /* T1 (dmrg.py:64-76): eigen-decomposition of a Hermitian (n x n) row-major matrix, in place:
  * on exit row i of `a` is the i-th eigenvector (ascending eigenvalues in w). */
 size_t pdmrg_heevd_workspace_bytes(int dtype, int n);

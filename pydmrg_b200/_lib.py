@@ -58,6 +58,7 @@ def _load():
         "pdmrg_vec_scratch_bytes": (sz, [i]),
         "pdmrg_svd_workspace_bytes": (sz, [i, i, i, i]),
         "pdmrg_svd": (i, [i, i, i, vp, vp, vp, vp, i, vp, sz, vp, vp]),
+        "pdmrg_svd_topk": (i, [i, i, i, i, vp, vp, vp, vp, i, vp, sz, vp, vp]),
         "pdmrg_heevd_workspace_bytes": (sz, [i, i]),
         "pdmrg_heevd": (i, [i, i, vp, vp, vp, sz, vp, vp]),
     }

@@ -41,13 +41,13 @@ class Context:
         self.npdtype = D.np_dtype(self.code)
         self.ws = D.Workspace(self.device)
         self.svd_ws = D.Workspace(self.device)
-        # 'auto': LAPACK-grade gesvd for small cuts, the 7x faster Gram/eigh/QR route from 1024^2 up
+        # 'auto': cuSOLVER gesvd for small cuts, the Gram/eigh/QR route (5-8x faster) from 128 up
         self.svd_method = {"gesvd": D.SVD_GESVD, "gesvdj": D.SVD_GESVDJ, "gram": D.SVD_GRAM, "auto": -1}[svd_method]
 
     def svd_method_for(self, rows, cols):
         if self.svd_method >= 0:
             return self.svd_method
-        return D.SVD_GRAM if min(rows, cols) >= 1024 else D.SVD_GESVD
+        return D.SVD_GRAM if min(rows, cols) >= 128 else D.SVD_GESVD
 
     # -- conversions ---------------------------------------------------------------------
     def dev(self, a):

@@ -9,6 +9,7 @@
 #include <cusolverDn.h>
 #include <dlfcn.h>
 #include <mutex>
+#include <vector>
 
 namespace pdmrg {
 namespace {
@@ -140,9 +141,11 @@ int svd_layout(Solver* s, int dtype, int rows, int cols, int method, SvdLayout* 
 // For a (rows x cols), rows <= cols:  G = a a^H (DMMA GEMM) -> heevd -> U (exactly unitary);
 // Y = a^H U = V S has orthogonal columns of norm S_i; its Householder QR  Y = Q R  gives an
 // exactly isometric V = Q phase with S_i = |R_ii|.  Both factors are isometries to machine
-// precision; the reconstruction error is O(eps S_0^2 / S_i) in the direction of S_i, i.e. at
-// most of the order of the weight a chi-truncation discards anyway.  ~7x faster than gesvd at
-// 2048 x 2048 complex128 (tools/svd_bench.py).
+// precision.  A single Gram level resolves direction i only to eps S_0^2 / S_i, so the tail
+// (S_i < 1e-4 of the block's largest) is re-diagonalised from the Gram matrix of the PROJECTED
+// rows U_tail^H a, whose norm is 1e-8 S_0^2: up to two refinement levels bring the reconstruction
+// error to ~1e-12 S_0 for every singular value above 1e-12 S_0 (below that is rounding noise of
+// the input).  5-8x faster than gesvd at 2048 x 2048 complex128 (tools/svd_bench.py).
 template <bool CPLX>
 __global__ void qr_diag_kernel(const double* __restrict__ Y, long long ld, int k, double* __restrict__ S,
                                double* __restrict__ phase) {
@@ -180,9 +183,9 @@ __global__ void vh_from_q_kernel(const double* __restrict__ Qt, const double* __
 }
 
 struct GramLayout {
-  size_t G, Ut, mT, Y, tau, phase, lwork_bytes;
+  size_t G, Ut, mT, Y, tau, phase, tail, lwork_bytes;   // tail: 6 staging blocks for the refinement levels
   int lwork_elems;
-  size_t total() const { return G + Ut + mT + Y + tau + phase + lwork_bytes; }
+  size_t total() const { return G + Ut + mT + Y + tau + phase + 6 * tail + lwork_bytes; }
 };
 
 int gram_layout(Solver* s, int dtype, int rows, int cols, GramLayout* l) {
@@ -194,6 +197,7 @@ int gram_layout(Solver* s, int dtype, int rows, int cols, GramLayout* l) {
   l->Y = align_up((size_t)k * cols * eb, 256);
   l->tau = align_up((size_t)k * eb, 256);
   l->phase = align_up((size_t)k * 16, 256);
+  l->tail = l->Y;                                   // k x cols >= k x rows
   int lw_e = 0, lw_q = 0, lw_g = 0;
   cusolverStatus_t st;
   if (dtype == PDMRG_C128) {
@@ -213,55 +217,110 @@ int gram_layout(Solver* s, int dtype, int rows, int cols, GramLayout* l) {
   return 0;
 }
 
-// rows <= cols.  a is read only.
-int svd_gram_wide(Solver* s, int dtype, int rows, int cols, const void* a, void* U, double* S, void* Vh,
+int heevd_inplace(Solver* s, int dtype, int n, double* A, double* w, void* work, int lwork, int* info_dev) {
+  cusolverStatus_t st;
+  if (dtype == PDMRG_C128)
+    st = s->p_cusolverDnZheevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, (cuDoubleComplex*)A, n, w,
+                               (cuDoubleComplex*)work, lwork, info_dev);
+  else
+    st = s->p_cusolverDnDsyevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n, w, (double*)work, lwork, info_dev);
+  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("gram SVD: heevd failed (%d)", (int)st); return 1; }
+  count_launch();
+  return 0;
+}
+
+constexpr int GRAM_FALLBACK = 77;
+constexpr double GRAM_TAU2 = 1e-8;     // tail = eigenvalues below tau^2 = (1e-4)^2 of the block's largest
+constexpr int GRAM_MAX_REFINE = 1;   // one refinement level already reaches ~1e-12 S_0 (tau * sqrt(eps) = 1e-12)
+
+// rows <= cols.  a is read only.  Synchronises `stream` (reads eigenvalues to place the tail cuts).
+int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void* a, void* U, double* S, void* Vh,
                   unsigned char* ws, int* info_dev, cudaStream_t stream) {
   GramLayout l;
   if (gram_layout(s, dtype, rows, cols, &l)) return 1;
   const bool cplx = dtype == PDMRG_C128;
   const int k = rows;
-  double* G = reinterpret_cast<double*>(ws);
-  double* Ut = reinterpret_cast<double*>(ws + l.G);
-  double* mT = reinterpret_cast<double*>(ws + l.G + l.Ut);
-  double* Y = reinterpret_cast<double*>(ws + l.G + l.Ut + l.mT);
-  double* tau = reinterpret_cast<double*>(ws + l.G + l.Ut + l.mT + l.Y);
-  double* phase = reinterpret_cast<double*>(ws + l.G + l.Ut + l.mT + l.Y + l.tau);
-  void* work = ws + l.G + l.Ut + l.mT + l.Y + l.tau + l.phase;
+  const int nkeep = (keep <= 0 || keep > k) ? k : keep;      // leading singular triplets the caller uses
   const int E = cplx ? 2 : 1;
-  // G = a a^H
+  const size_t eb = elem_bytes(dtype);
+  unsigned char* q = ws;
+  auto take = [&](size_t bytes) { double* r = reinterpret_cast<double*>(q); q += bytes; return r; };
+  double* G = take(l.G);
+  double* Ut = take(l.Ut);
+  double* mT = take(l.mT);
+  double* Y = take(l.Y);
+  double* tau = take(l.tau);
+  double* phase = take(l.phase);
+  double* Uc = take(l.tail);      // conj of the tail rows of Ut
+  double* X2 = take(l.tail);      // tail rows of U^H a
+  double* G2 = take(l.tail);
+  double* W2 = take(l.tail);
+  double* Bt = take(l.tail);      // transposed tail of Ut
+  double* Ut2 = take(l.tail);
+  void* work = q;
+
+  // ---- level 0: G = a a^H, eigenvectors -> Ut (row a = u_a, descending eigenvalue)
   if (pdmrg_gemm_nt(dtype, rows, rows, cols, 1, a, cols, 0, a, cols, 0, 1, G, rows, 0, 1.0, 0.0, 0, stream)) return 1;
-  double* wtmp = Y;   // eigenvalues land in Y's storage for the moment (k doubles)
-  cusolverStatus_t st;
-  if (cplx) {
-    st = s->p_cusolverDnZheevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, rows, (cuDoubleComplex*)G, rows, wtmp,
-                               (cuDoubleComplex*)work, l.lwork_elems, info_dev);
-  } else {
-    st = s->p_cusolverDnDsyevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, rows, G, rows, wtmp, (double*)work,
-                               l.lwork_elems, info_dev);
-  }
-  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("gram SVD: heevd failed (%d)", (int)st); return 1; }
-  count_launch();
-  // row i of G (memory) = conj(eigenvector i of a a^H) (column-major solver on conj(G)), ascending.
-  // Ut[a, r] = u_{rows-1-a}[r]  (descending), conj restores the eigenvector of G itself
+  double* wdev = Y;               // eigenvalues (k doubles) parked in Y's storage
+  if (heevd_inplace(s, dtype, rows, G, wdev, work, l.lwork_elems, info_dev)) return 1;
+  // memory row i of G = conj(eigenvector i) (column-major solver on the row-major array), ascending
   if (pdmrg_permute4(dtype, G + (size_t)E * (rows - 1) * rows, Ut, 1, 1, k, rows, 0, 0, -(long long)rows, 1, 1, nullptr, 0, stream)) return 1;
-  // mT[c, r] = a[r, c]
-  if (pdmrg_permute4(dtype, a, mT, 1, 1, cols, rows, 0, 0, 1, cols, 0, nullptr, 0, stream)) return 1;
-  // Yrow[a, c] = sum_r Ut[a,r] conj(mT[c,r])  == column-major Y (cols x k) = a^H U
-  if (pdmrg_gemm_nt(dtype, k, cols, rows, 1, Ut, rows, 0, mT, rows, 0, 1, Y, cols, 0, 1.0, 0.0, 0, stream)) return 1;
-  if (cplx) st = s->p_cusolverDnZgeqrf(s->handle, cols, k, (cuDoubleComplex*)Y, cols, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
-  else st = s->p_cusolverDnDgeqrf(s->handle, cols, k, Y, cols, tau, (double*)work, l.lwork_elems, info_dev);
+  if (pdmrg_permute4(dtype, a, mT, 1, 1, cols, rows, 0, 0, 1, cols, 0, nullptr, 0, stream)) return 1;   // mT[c,r] = a[r,c]
+  std::vector<double> lam(k);
+  int info_host = 0;
+  PDMRG_CHECK_CUDA(cudaMemcpyAsync(lam.data(), wdev, (size_t)k * 8, cudaMemcpyDeviceToHost, stream));
+  PDMRG_CHECK_CUDA(cudaMemcpyAsync(&info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));
+  // cuSOLVER's divide-and-conquer heevd can fail (info > 0) on exactly rank-deficient Gram matrices
+  // (zero-padded tensors right after a chi increase): hand the call to gesvd
+  if (info_host != 0) return GRAM_FALLBACK;
+  const double lam_top = lam[k - 1];
+  // ---- refinement of the small-singular-value tail: the Gram matrix of the projected rows
+  //      U_tail^H a has norm (tau S_0)^2, so its eigen-decomposition resolves what level 0 cannot
+  int t_prev = 0, nblk = k;       // current block = rows [t_prev, k), eigenvalues lam[0..nblk) ascending
+  for (int level = 0; level < GRAM_MAX_REFINE; ++level) {
+    const double top = lam[nblk - 1];
+    if (!(top > 0.0) || top < 1e-28 * lam_top) break;
+    int keep = 0;
+    while (keep < nblk && lam[nblk - 1 - keep] >= GRAM_TAU2 * top) ++keep;
+    const int t = t_prev + keep, nt = k - t;
+    if (nt < 2 || t >= nkeep) break;      // every singular vector the caller keeps is already resolved
+    // Uc[i,r] = conj(Ut[t+i,r]);  X2 = Uc mT^T = rows t.. of U^H a
+    if (pdmrg_permute4(dtype, Ut + (size_t)E * t * rows, Uc, 1, 1, nt, rows, 0, 0, rows, 1, 1, nullptr, 0, stream)) return 1;
+    if (pdmrg_gemm_nt(dtype, nt, cols, rows, 1, Uc, rows, 0, mT, rows, 0, 0, X2, cols, 0, 1.0, 0.0, 0, stream)) return 1;
+    if (pdmrg_gemm_nt(dtype, nt, nt, cols, 1, X2, cols, 0, X2, cols, 0, 1, G2, nt, 0, 1.0, 0.0, 0, stream)) return 1;
+    if (heevd_inplace(s, dtype, nt, G2, wdev, work, l.lwork_elems, info_dev)) return 1;
+    PDMRG_CHECK_CUDA(cudaMemcpyAsync(&info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PDMRG_CHECK_CUDA(cudaMemcpyAsync(lam.data(), wdev, (size_t)nt * 8, cudaMemcpyDeviceToHost, stream));
+    PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (info_host != 0) return GRAM_FALLBACK;
+    // W2[j,i] = w_j[i] (descending j);  Bt[r,i] = Ut[t+i,r];  Ut2[j,r] = sum_i W2[j,i] Bt[r,i]
+    if (pdmrg_permute4(dtype, G2 + (size_t)E * (nt - 1) * nt, W2, 1, 1, nt, nt, 0, 0, -(long long)nt, 1, 1, nullptr, 0, stream)) return 1;
+    if (pdmrg_permute4(dtype, Ut + (size_t)E * t * rows, Bt, 1, 1, rows, nt, 0, 0, 1, rows, 0, nullptr, 0, stream)) return 1;
+    if (pdmrg_gemm_nt(dtype, nt, rows, nt, 1, W2, nt, 0, Bt, nt, 0, 0, Ut2, rows, 0, 1.0, 0.0, 0, stream)) return 1;
+    PDMRG_CHECK_CUDA(cudaMemcpyAsync(Ut + (size_t)E * t * rows, Ut2, (size_t)nt * rows * eb, cudaMemcpyDeviceToDevice, stream));
+    t_prev = t; nblk = nt;
+  }
+  // ---- Y = a^H U (column-major cols x k == row-major Yrow[a,c] = sum_r Ut[a,r] conj(mT[c,r])), Householder QR
+  //      (only the nkeep leading columns: the discarded triplets are never formed)
+  const int nq = nkeep;
+  if (pdmrg_gemm_nt(dtype, nq, cols, rows, 1, Ut, rows, 0, mT, rows, 0, 1, Y, cols, 0, 1.0, 0.0, 0, stream)) return 1;
+  cusolverStatus_t st;
+  if (cplx) st = s->p_cusolverDnZgeqrf(s->handle, cols, nq, (cuDoubleComplex*)Y, cols, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+  else st = s->p_cusolverDnDgeqrf(s->handle, cols, nq, Y, cols, tau, (double*)work, l.lwork_elems, info_dev);
   if (st != CUSOLVER_STATUS_SUCCESS) { set_error("gram SVD: geqrf failed (%d)", (int)st); return 1; }
-  if (cplx) qr_diag_kernel<true><<<(k + 127) / 128, 128, 0, stream>>>(Y, cols, k, S, phase);
-  else qr_diag_kernel<false><<<(k + 127) / 128, 128, 0, stream>>>(Y, cols, k, S, phase);
+  if (nq < k) PDMRG_CHECK_CUDA(cudaMemsetAsync(S + nq, 0, (size_t)(k - nq) * 8, stream));
+  if (cplx) qr_diag_kernel<true><<<(nq + 127) / 128, 128, 0, stream>>>(Y, cols, nq, S, phase);
+  else qr_diag_kernel<false><<<(nq + 127) / 128, 128, 0, stream>>>(Y, cols, nq, S, phase);
   PDMRG_CHECK_LAUNCH();
-  if (cplx) st = s->p_cusolverDnZungqr(s->handle, cols, k, k, (cuDoubleComplex*)Y, cols, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
-  else st = s->p_cusolverDnDorgqr(s->handle, cols, k, k, Y, cols, tau, (double*)work, l.lwork_elems, info_dev);
+  if (cplx) st = s->p_cusolverDnZungqr(s->handle, cols, nq, nq, (cuDoubleComplex*)Y, cols, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+  else st = s->p_cusolverDnDorgqr(s->handle, cols, nq, nq, Y, cols, tau, (double*)work, l.lwork_elems, info_dev);
   if (st != CUSOLVER_STATUS_SUCCESS) { set_error("gram SVD: ungqr failed (%d)", (int)st); return 1; }
   count_launch(3);
-  int grid = (int)(((long long)k * cols + 255) / 256);
+  int grid = (int)(((long long)nq * cols + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  if (cplx) vh_from_q_kernel<true><<<grid, 256, 0, stream>>>(Y, phase, k, cols, (double*)Vh);
-  else vh_from_q_kernel<false><<<grid, 256, 0, stream>>>(Y, phase, k, cols, (double*)Vh);
+  if (cplx) vh_from_q_kernel<true><<<grid, 256, 0, stream>>>(Y, phase, nq, cols, (double*)Vh);
+  else vh_from_q_kernel<false><<<grid, 256, 0, stream>>>(Y, phase, nq, cols, (double*)Vh);
   PDMRG_CHECK_LAUNCH();
   count_launch();
   // U[r, a] = Ut[a, r]
@@ -290,15 +349,26 @@ extern "C" size_t pdmrg_svd_workspace_bytes(int dtype, int rows, int cols, int m
     const size_t eb = elem_bytes(dtype);
     // transposed problem (rows > cols): a^T, U', Vh' staging
     const size_t extra = rows > cols ? 3 * align_up((size_t)rows * cols * eb, 256) : 0;
-    return g.total() + extra + 256;
+    SvdLayout fb;                                   // gesvd fallback shares the workspace
+    if (svd_layout(s, dtype, rows, cols, 0, &fb)) return 0;
+    const size_t need = g.total() + extra + 256;
+    return need > fb.total() + 256 ? need : fb.total() + 256;
   }
   SvdLayout l;
   if (svd_layout(s, dtype, rows, cols, method, &l)) return 0;
   return l.total() + 256;
 }
 
+extern "C" int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, void* U, double* S, void* Vh, int method,
+                              void* workspace, size_t workspace_bytes, int* info_dev, void* stream_);
+
 extern "C" int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* Vh, int method,
                          void* workspace, size_t workspace_bytes, int* info_dev, void* stream_) {
+  return pdmrg_svd_topk(dtype, rows, cols, 0, a, U, S, Vh, method, workspace, workspace_bytes, info_dev, stream_);
+}
+
+extern "C" int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, void* U, double* S, void* Vh, int method,
+                              void* workspace, size_t workspace_bytes, int* info_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Solver* s = get_solver();
   if (!s) return 1;
@@ -309,13 +379,20 @@ extern "C" int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double
     PDMRG_REQUIRE(workspace_bytes >= pdmrg_svd_workspace_bytes(dtype, rows, cols, 2), "pdmrg_svd: workspace too small");
     if (s->p_cusolverDnSetStream(s->handle, stream) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnSetStream failed"); return 1; }
     unsigned char* w8 = static_cast<unsigned char*>(workspace);
-    if (rows <= cols) return svd_gram_wide(s, dtype, rows, cols, a, U, S, Vh, w8, info_dev, stream);
+    int rc;
+    if (rows <= cols) {
+      rc = svd_gram_wide(s, dtype, rows, cols, keep, a, U, S, Vh, w8, info_dev, stream);
+      if (rc != GRAM_FALLBACK) return rc;
+      return pdmrg_svd(dtype, rows, cols, a, U, S, Vh, 0, workspace, workspace_bytes, info_dev, stream_);
+    }
     // a^T = U' S Vh'  =>  a = Vh'^T S U'^T
     const size_t blk = align_up((size_t)rows * cols * elem_bytes(dtype), 256);
     void* aT = w8; void* Up = w8 + blk; void* Vhp = w8 + 2 * blk;
     const int k = cols;
     if (pdmrg_permute4(dtype, a, aT, 1, 1, cols, rows, 0, 0, 1, cols, 0, nullptr, 0, stream)) return 1;
-    if (svd_gram_wide(s, dtype, cols, rows, aT, Up, S, Vhp, w8 + 3 * blk, info_dev, stream)) return 1;
+    rc = svd_gram_wide(s, dtype, cols, rows, keep, aT, Up, S, Vhp, w8 + 3 * blk, info_dev, stream);
+    if (rc == GRAM_FALLBACK) return pdmrg_svd(dtype, rows, cols, a, U, S, Vh, 0, workspace, workspace_bytes, info_dev, stream_);
+    if (rc) return 1;
     if (pdmrg_permute4(dtype, Vhp, U, 1, 1, rows, k, 0, 0, 1, rows, 0, nullptr, 0, stream)) return 1;    // U[r,j] = Vh'[j,r]
     if (pdmrg_permute4(dtype, Up, Vh, 1, 1, k, cols, 0, 0, 1, k, 0, nullptr, 0, stream)) return 1;       // Vh[j,c] = U'[c,j]
     return 0;

@@ -274,8 +274,9 @@ SVD_GESVDJ = 1
 SVD_GRAM = 2
 
 
-def svd(a, workspace, method=SVD_GESVD):
-    """Thin SVD of a row-major (rows, cols) CUDA matrix (destroyed).  Returns U, S, Vh."""
+def svd(a, workspace, method=SVD_GESVD, keep=0):
+    """Thin SVD of a row-major (rows, cols) CUDA matrix (destroyed).  Returns U, S, Vh, info.
+    ``keep`` > 0: only the leading ``keep`` triplets are needed (lets the Gram route skip work)."""
     code = dtype_code(a)
     rows, cols = a.shape
     k = min(rows, cols)
@@ -287,8 +288,8 @@ def svd(a, workspace, method=SVD_GESVD):
     if nb == 0:
         check(1, "pdmrg_svd_workspace_bytes")
     ws = workspace.get(nb)
-    check(lib.pdmrg_svd(code, rows, cols, _ptr(a), _ptr(U), _ptr(S), _ptr(Vh), method, _ptr(ws), ws.numel(),
-                        _ptr(info), _stream()), "pdmrg_svd")
+    check(lib.pdmrg_svd_topk(code, rows, cols, int(keep), _ptr(a), _ptr(U), _ptr(S), _ptr(Vh), method, _ptr(ws),
+                             ws.numel(), _ptr(info), _stream()), "pdmrg_svd")
     return U, S, Vh, info
 
 

@@ -38,6 +38,26 @@ def _log(level, msg):
         print(msg)
 
 
+class _Tick:
+    """Optional wall-clock profile of a step (stats['profile'] = True): synchronises, so it is off
+    by default."""
+
+    def __init__(self, on):
+        self.on = bool(on)
+        if self.on:
+            import time
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def lap(self, stats, key):
+        if self.on:
+            import time
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            stats[key] = stats.get(key, 0.0) + now - self.t
+            self.t = now
+
+
 # ---------------------------------------------------------------------------------------
 # renormalisation wrappers with the reference's signatures
 # ---------------------------------------------------------------------------------------
@@ -113,10 +133,14 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
     proto = mpsL[0][site]
     d1, Dl, _ = proto.shape
     d2, _, Dr = mpsL[0][site + 1].shape
+    prof = stats is not None and stats.get("profile")
+    tick = _Tick(prof)
     E, v, _ = calc_eigs(mpsL, W, F, site, 1, alg=alg, oneSite=False, edgePreserveState=False, ctx=ctx,
                         stats=stats, return_device=True, **solver)
+    tick.lap(stats, "t_eig")
     psi = v[:, 0].contiguous()
     A, B, S, EE, EEs = svd_truncate(psi, (d1, d2, Dl, Dr), mbd, ctx, absorb=direction)
+    tick.lap(stats, "t_svd")
     mpsL[0][site] = like(A, proto)
     mpsL[0][site + 1] = like(B, proto)
     if direction == "right":
@@ -127,6 +151,7 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
         for m in range(len(W)):
             out = D.env_update_left(B, W[m][site + 1], ctx.dev(F[m][site + 2]), None, ctx.ws)
             F[m][site + 1] = like(out, proto)
+    tick.lap(stats, "t_env")
     return E, mpsL, F, EE, EEs, S
 
 
@@ -315,14 +340,14 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
                 if calcLeftState:
                     mpslList = mps_tools.increase_all_mbd(mpslList, mbdi)
         else:
-            # an in-memory mpsList (lists of ndarrays), gauge at site 0
-            mpsList = [[np.array(t) for t in M] for M in (initGuess[0] if calcLeftState else initGuess)]
-            gSite = 0
+            # an in-memory mpsList (lists of ndarrays), gauge at site 0 -- or (mpsList, gaugeSite)
+            guess, gSite = (initGuess if (isinstance(initGuess, tuple) and len(initGuess) == 2
+                                          and np.ndim(initGuess[1]) == 0) else (initGuess, 0))
+            mpsList = [[np.array(t) for t in M] for M in (guess[0] if calcLeftState else guess)]
+            mpsList = mps_tools.increase_all_mbd(mpsList, mbdi)
             if calcLeftState:
-                mpslList = [[np.array(t) for t in M] for M in initGuess[1]]
-                glSite = 0
-            if mbdInd != 0:
-                mpsList = mps_tools.increase_all_mbd(mpsList, mbdi)
+                mpslList = mps_tools.increase_all_mbd([[np.array(t) for t in M] for M in guess[1]], mbdi)
+                glSite = gSite
         gSite = int(gSite)
         mpsList = [[ctx.dev(t) for t in M] for M in mpsList]
         if calcLeftState:

@@ -1,0 +1,91 @@
+"""s-field / parameter scans: independent DMRG points distributed over GPUs.
+
+The reference's scan scripts are serial continuations -- every point warm-starts from the previous
+point's saved MPS (pydmrg/scripts/asep/current/bondDimConv.py:19-27, multipleStates.py:114-129).
+Here the list of points is cut into ``world`` contiguous blocks (one per GPU / rank); the
+continuation is kept INSIDE a block (first point of a block cold-starts through the chi ramp), so
+there is no data-path communication at all; results are gathered once at the end.
+
+    torchrun --nproc-per-node 8 -m pydmrg_b200.scan --N 50 --chi 256 --points 64
+"""
+import time
+
+import numpy as np
+
+from . import mpo as mpo_lib
+from .parallel import gather_scan, scan_block
+
+
+def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
+             twoSite=True, dtype="c128", continuation=True, stats=None, **solver):
+    """Run ``run_dmrg(mpo_of(v), mbd=...)`` for every v in ``values`` (this rank's block only).
+
+    Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
+    rank's points, block: (lo, hi))."""
+    from .dmrg import run_dmrg
+    n = len(values)
+    lo, hi = scan_block(n, rank, world)
+    E_loc, EE_loc, secs = [], [], []
+    prev = None
+    for idx in range(lo, hi):
+        mpo = mpo_of(values[idx])
+        t0 = time.perf_counter()
+        if prev is None or not continuation:
+            # cold start: chi ramp with in-memory continuation between stages
+            guess = None
+            for chi in list(ramp) + [mbd]:
+                if chi > mbd:
+                    continue
+                out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if chi == mbd else 1, minIter=minIter,
+                               initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **solver)
+                guess = _grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd]))
+        else:
+            out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,
+                           dtype=dtype, returnState=True, stats=stats, **solver)
+        secs.append(time.perf_counter() - t0)
+        E_loc.append(out[0]); EE_loc.append(out[1])
+        prev = out[-1]
+    return {"E": gather_scan(E_loc, n, rank, world, dist), "EE": gather_scan(EE_loc, n, rank, world, dist),
+            "sec": secs, "block": (lo, hi)}
+
+
+def _grow(mpsList, chi):
+    from . import mps as mps_tools
+    return mps_tools.increase_all_mbd([[np.array(t) for t in M] for M in mpsList], chi)
+
+
+def main():
+    import argparse, json, os
+    import torch
+    import torch.distributed as dist
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=50)
+    ap.add_argument("--chi", type=int, default=256)
+    ap.add_argument("--points", type=int, default=64)
+    ap.add_argument("--smin", type=float, default=-0.5)
+    ap.add_argument("--smax", type=float, default=0.5)
+    ap.add_argument("--max-iter", type=int, default=4)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    if world > 1:
+        dist.init_process_group("nccl")
+    s_vals = np.linspace(args.smin, args.smax, args.points)        # scripts/asep/current/bondDimConv.py:10
+    mpo_of = lambda s: mpo_lib.asep_mpo(args.N, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
+                          "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt,
+                          "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

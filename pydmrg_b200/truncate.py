@@ -35,8 +35,8 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     m = ctx.empty(rows, cols)
     # m[(k,n),(q,s)] = psi[n,q,k,s]      (mps_tools.py:105-107)
     D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
-    U, S, Vh, info = D.svd(m, ctx.svd_ws, ctx.svd_method_for(rows, cols))
     kfull = min(rows, cols)
+    U, S, Vh, info = D.svd(m, ctx.svd_ws, ctx.svd_method_for(rows, cols), keep=min(int(mbd), kfull))
     Sh = S.cpu().numpy()                                        # sync; also validates the factorisation
     if int(info.item()) != 0:
         raise ArithmeticError("cuSOLVER SVD did not converge (info=%d)" % int(info.item()))
@@ -44,7 +44,9 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     EE, EEs, Sn = calc_entanglement(Sh[:k])
     scale = None
     if absorb is not None:
-        full = np.sqrt(np.dot(Sh, Sh))
+        # ||psi|| (the Gram route returns only the kept singular values; Davidson vectors are unit norm
+        # up to rounding, and the absorbed scale only sets the norm of the next guess)
+        full = max(np.sqrt(np.dot(Sh, Sh)), np.sqrt(np.dot(Sh[:k], Sh[:k])))
         scale = torch.from_numpy(np.ascontiguousarray(Sn * full)).to(ctx.device)
     A = ctx.empty(d1, Dl, k)
     B = ctx.empty(d2, k, Dr)

@@ -269,26 +269,30 @@ def test_vec_ops(D, real):
 
 @pytest.mark.parametrize("real", [False, True])
 def test_svd_gram_decaying_spectrum(D, ws, real):
-    """Method 2 (Gram + heevd + Householder QR) on a physical-looking spectrum spanning 12 decades:
-    both factors exact isometries; Schmidt WEIGHTS S_i^2 (what EE / EEs are made of) accurate to
-    eps*S_0^2 uniformly; S_i itself and the reconstruction to eps*S_0^2/S_i, i.e. 1e-9 for
-    everything above 1e-6 of the largest value (the error model stated in csrc/solver.cu)."""
+    """Method 2 (Gram + heevd + Householder QR + tail refinement) on a physical-looking spectrum
+    spanning 14 decades: both factors exact isometries, singular values and reconstruction to
+    ~1e-12 S_0 (the error model stated in csrc/solver.cu)."""
     rng = np.random.default_rng(5)
     n = 192
     mk = (lambda *s: rng.standard_normal(s)) if real else (lambda *s: crand(rng, *s))
     u, _ = np.linalg.qr(mk(n, n)); v, _ = np.linalg.qr(mk(n, n))
-    s = np.exp(-np.arange(n) * (np.log(1e12) / n))
+    s = np.exp(-np.arange(n) * (np.log(1e14) / n))
     a = (u * s) @ v.conj().T
     U, S, Vh, info = D.svd(dev(a.copy()), ws, D.SVD_GRAM)
     torch.cuda.synchronize()
     U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
     assert np.allclose(U.conj().T @ U, np.eye(n), atol=1e-12) and np.allclose(Vh @ Vh.conj().T, np.eye(n), atol=1e-12)
     assert np.max(np.abs(S ** 2 - s ** 2)) < 1e-13 * s[0] ** 2
-    k = int(np.sum(s / s[0] >= 1e-6))
-    assert np.max(np.abs(S[:k] - s[:k])) < 1e-9 * s[0]
-    rec = (U[:, :k] * S[:k]) @ Vh[:k]
-    ref = (u[:, :k] * s[:k]) @ v.conj().T[:k]
-    assert rel(rec, ref) < 1e-9
+    assert np.max(np.abs(S - s)) < 1e-11 * s[0]
+    assert rel((U * S) @ Vh, a) < 1e-11
+    # rectangular + rank deficient: exact zeros in the tail must not break the refinement
+    b = a[:, :64] @ mk(64, 300)
+    U, S, Vh, info = D.svd(dev(b.copy()), ws, D.SVD_GRAM)
+    torch.cuda.synchronize()
+    U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+    assert info.item() == 0 and np.all(np.isfinite(U)) and np.all(np.isfinite(Vh))
+    assert rel((U * S) @ Vh, b) < 1e-11
+    assert np.allclose(Vh @ Vh.conj().T, np.eye(n), atol=1e-11) and np.allclose(U.conj().T @ U, np.eye(n), atol=1e-11)
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])

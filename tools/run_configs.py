@@ -1,0 +1,63 @@
+"""Run the BASELINE.json configurations end to end on one GPU and print timings
+(development / evidence tool; results are summarised in profiles/README.md)."""
+import json, os, sys, time, tempfile
+import numpy as np, torch
+sys.path.insert(0, ".")
+from pydmrg_b200 import core, dmrg, env, mpo as M, mps as mps_tools
+
+which = sys.argv[1:] or ["cfg0", "cfg1", "cfg3pt"]
+out = {}
+
+SVD = os.environ.get("PDMRG_SVD", "auto")
+
+
+def timed_sweeps(mpo, chi, dtype, n_sweeps, seed=0, two_site=True, sched=None, res_tol=None):
+    ctx = core.Context(dtype, svd_method=SVD)
+    N = len(mpo[0])
+    np.random.seed(seed)
+    tmp = tempfile.mkdtemp()
+    t0 = time.perf_counter()
+    if sched:
+        r = dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=two_site, ctx=ctx)
+        mpsL, g = mps_tools.load_mps(os.path.join(tmp, "st_mbd%d" % (len(sched) - 1)))
+        mpsL = mps_tools.increase_all_mbd(mpsL, chi)
+    else:
+        mpsL = mps_tools.make_all_mps_right(mps_tools.create_all_mps(N, chi, 1))
+    t_prep = time.perf_counter() - t0
+    mpsL = [[ctx.dev(t) for t in mpsL[0]]]
+    F = env.calc_env(mpsL[0], mpo, chi, gaugeSite=0, ctx=ctx)
+    res = []
+    for s in range(n_sweeps):
+        stats = {"profile": bool(os.environ.get("PDMRG_PROFILE"))}
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        if two_site:
+            E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, res_tol=res_tol)
+        else:
+            E, mpsL, F, EE, EEs = dmrg.rightSweep(mpsL, mpo, F, s, ctx=ctx, stats=stats)
+            E, mpsL, F, EE, EEs = dmrg.leftSweep(mpsL, mpo, F, s, ctx=ctx, stats=stats)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        res.append({"sweep": s, "sec": dt, "E": complex(E).real, "EE": float(EE), "n_matvec": stats.get("n_matvec"), "cycles": stats.get("cycles"),
+                    "t_eig": stats.get("t_eig"), "t_svd": stats.get("t_svd"), "t_env": stats.get("t_env")})
+        print("   sweep", res[-1], flush=True)
+    return {"prep_sec": t_prep, "sweeps": res}
+
+if "cfg0" in which:
+    mpo = M.asep_mpo(10, (0.35, 0, 1, 0, 2 / 3, 0, -0.5))
+    np.random.seed(0); t0 = time.perf_counter(); st = {}
+    r = dmrg.run_dmrg(mpo, mbd=10, tol=1e-8, maxIter=10, stats=st)
+    out["cfg0"] = {"sec": time.perf_counter() - t0, "E": complex(r[0]).real, "n_matvec": st["n_matvec"]}
+    print("cfg0", out["cfg0"], flush=True)
+if "cfg1" in which:
+    print("cfg1: Heisenberg N=100 chi=256 f64 two-site", flush=True)
+    out["cfg1"] = timed_sweeps(M.heisenberg_mpo(100), 256, "f64", 3, sched=[16, 64])
+if "cfg3pt" in which:
+    print("cfg3 point: ASEP N=50 chi=256 c128 one s value, two-site", flush=True)
+    out["cfg3pt"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 3, sched=[16, 64])
+if "cfg3pt1" in which:
+    print("cfg3 point: ASEP N=50 chi=256 c128 one s value, ONE-site (the reference's finite algorithm)", flush=True)
+    out["cfg3pt1"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 3, two_site=False, sched=[16, 64])
+if "cfg2" in which:
+    print("cfg2: TASEP N=100 chi=1024 c128 two-site, one sweep after a [16,64,256] ramp", flush=True)
+    out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", 1, sched=[16, 64, 256])
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/run_configs.json", "w"), indent=1)
