@@ -152,9 +152,9 @@ size_t pdmrg_vec_scratch_bytes(int m);
  * T2 (tools/mps_tools.py:98-120): thin SVD of a row-major (rows x cols) matrix a:
  *   a = U diag(S) Vh,  U (rows x k) row-major, S (k) descending, Vh (k x cols) row-major,
  *   k = min(rows, cols).  `a` is destroyed (methods 0, 1).  method: 0 = QR-iteration (gesvd),
- *   1 = Jacobi (gesvdj), 2 = Gram matrix (DMMA GEMM) + heevd + Householder QR with up to two tail
- *   refinement levels: both factors are exact isometries, reconstruction error ~1e-12*S_0 (see
- *   csrc/solver.cu); 5-8x faster at 2048^2; this method SYNCHRONISES the stream.  info_dev: one int
+ *   1 = Jacobi (gesvdj), 2 = Gram matrix (DMMA GEMM) + heevd + Householder QR with a gated tail
+ *   refinement level: both factors are exact isometries, reconstruction error <= 1e-9*S_0
+ *   (typically 1e-12, see csrc/solver.cu); 5-10x faster at 2048^2; SYNCHRONISES the stream.  info_dev: one int
  *   (device).  cuSOLVER is loaded on first use. */
 size_t pdmrg_svd_workspace_bytes(int dtype, int rows, int cols, int method);
 int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* Vh,
@@ -164,6 +164,15 @@ int pdmrg_svd(int dtype, int rows, int cols, void* a, void* U, double* S, void* 
  * rows [0, keep) are defined for method 2 (S[keep:] = 0); methods 0 and 1 compute everything. */
 int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, void* U, double* S, void* Vh,
                    int method, void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
+/* Left singular basis of a row-major X (n x c) for projective truncation of a moving centre:
+ * Ut (n x n, row a = eigenvector u_a of X X^H, eigenvalues descending) and lam[a] = S_a^2, with the
+ * small-singular-value tail re-diagonalised from the projected Gram matrix (directions and
+ * weights accurate to ~1e-12 S_0, see csrc/solver.cu) whenever one of the `keep` leading vectors
+ * lies in it.  X is read-only.  SYNCHRONISES the stream.  Returns 77 if cuSOLVER's heevd did not
+ * converge (caller falls back to pdmrg_svd method 0). */
+size_t pdmrg_left_basis_workspace_bytes(int dtype, int n, int c);
+int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X, void* Ut, double* lam,
+                     void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
 /* T1 (dmrg.py:64-76): eigen-decomposition of a Hermitian (n x n) row-major matrix, in place:
  * on exit row i of `a` is the i-th eigenvector (ascending eigenvalues in w). */
 size_t pdmrg_heevd_workspace_bytes(int dtype, int n);

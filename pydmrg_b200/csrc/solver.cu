@@ -143,9 +143,11 @@ int svd_layout(Solver* s, int dtype, int rows, int cols, int method, SvdLayout* 
 // exactly isometric V = Q phase with S_i = |R_ii|.  Both factors are isometries to machine
 // precision.  A single Gram level resolves direction i only to eps S_0^2 / S_i, so the tail
 // (S_i < 1e-4 of the block's largest) is re-diagonalised from the Gram matrix of the PROJECTED
-// rows U_tail^H a, whose norm is 1e-8 S_0^2: up to two refinement levels bring the reconstruction
-// error to ~1e-12 S_0 for every singular value above 1e-12 S_0 (below that is rounding noise of
-// the input).  5-8x faster than gesvd at 2048 x 2048 complex128 (tools/svd_bench.py).
+// rows U_tail^H a, whose norm is 1e-8 S_0^2: one refinement level brings the reconstruction error
+// to ~1e-12 S_0 for every singular value above 1e-12 S_0 (below that is rounding noise of the
+// input).  The level is skipped when the accurate row norms |u_i^H a| show that the kept tail
+// vectors cannot be off by more than 1e-9 S_0 in total.  5-10x faster than gesvd at 2048 x 2048
+// complex128 (tools/svd_bench.py).
 template <bool CPLX>
 __global__ void qr_diag_kernel(const double* __restrict__ Y, long long ld, int k, double* __restrict__ S,
                                double* __restrict__ phase) {
@@ -182,6 +184,25 @@ __global__ void vh_from_q_kernel(const double* __restrict__ Qt, const double* __
   }
 }
 
+// G_ii += rel * mean(diag G): lifts entries that underflowed towards the denormal range (rows of
+// norm ~1e-85 appear after zero-padding in a chi ramp and make cuSOLVER's heevd fail to converge);
+// rel = 1e-28 is far below every accuracy the factorisation delivers.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) shift_diag_kernel(double* G, int n, double rel) {
+  __shared__ double sm[256];
+  constexpr int E = CPLX ? 2 : 1;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += G[(size_t)E * ((size_t)i * n + i)];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double delta = rel * fabs(sm[0]) / n;
+  for (int i = threadIdx.x; i < n; i += 256) G[(size_t)E * ((size_t)i * n + i)] += delta;
+}
+
 struct GramLayout {
   size_t G, Ut, mT, Y, tau, phase, tail, lwork_bytes;   // tail: 6 staging blocks for the refinement levels
   int lwork_elems;
@@ -197,7 +218,7 @@ int gram_layout(Solver* s, int dtype, int rows, int cols, GramLayout* l) {
   l->Y = align_up((size_t)k * cols * eb, 256);
   l->tau = align_up((size_t)k * eb, 256);
   l->phase = align_up((size_t)k * 16, 256);
-  l->tail = l->Y;                                   // k x cols >= k x rows
+  l->tail = align_up((size_t)k * (size_t)(cols > rows ? cols : rows) * eb, 256);   // staging blocks: up to k x max(rows, cols)
   int lw_e = 0, lw_q = 0, lw_g = 0;
   cusolverStatus_t st;
   if (dtype == PDMRG_C128) {
@@ -217,7 +238,11 @@ int gram_layout(Solver* s, int dtype, int rows, int cols, GramLayout* l) {
   return 0;
 }
 
-int heevd_inplace(Solver* s, int dtype, int n, double* A, double* w, void* work, int lwork, int* info_dev) {
+int heevd_inplace(Solver* s, int dtype, int n, double* A, double* w, void* work, int lwork, int* info_dev,
+                  cudaStream_t stream) {
+  if (dtype == PDMRG_C128) shift_diag_kernel<true><<<1, 256, 0, stream>>>(A, n, 1e-28);
+  else shift_diag_kernel<false><<<1, 256, 0, stream>>>(A, n, 1e-28);
+  PDMRG_CHECK_LAUNCH();
   cusolverStatus_t st;
   if (dtype == PDMRG_C128)
     st = s->p_cusolverDnZheevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, (cuDoubleComplex*)A, n, w,
@@ -234,8 +259,10 @@ constexpr double GRAM_TAU2 = 1e-8;     // tail = eigenvalues below tau^2 = (1e-4
 constexpr int GRAM_MAX_REFINE = 1;   // one refinement level already reaches ~1e-12 S_0 (tau * sqrt(eps) = 1e-12)
 
 // rows <= cols.  a is read only.  Synchronises `stream` (reads eigenvalues to place the tail cuts).
+// basis_only: stop after the (refined) left basis -- U receives Ut (k x rows, row a = eigenvector u_a of
+// a a^H, descending) and S the eigenvalues lambda_a = S_a^2 (refined in the tail); Vh is not touched.
 int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void* a, void* U, double* S, void* Vh,
-                  unsigned char* ws, int* info_dev, cudaStream_t stream) {
+                  unsigned char* ws, int* info_dev, cudaStream_t stream, bool basis_only = false) {
   GramLayout l;
   if (gram_layout(s, dtype, rows, cols, &l)) return 1;
   const bool cplx = dtype == PDMRG_C128;
@@ -262,7 +289,7 @@ int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void
   // ---- level 0: G = a a^H, eigenvectors -> Ut (row a = u_a, descending eigenvalue)
   if (pdmrg_gemm_nt(dtype, rows, rows, cols, 1, a, cols, 0, a, cols, 0, 1, G, rows, 0, 1.0, 0.0, 0, stream)) return 1;
   double* wdev = Y;               // eigenvalues (k doubles) parked in Y's storage
-  if (heevd_inplace(s, dtype, rows, G, wdev, work, l.lwork_elems, info_dev)) return 1;
+  if (heevd_inplace(s, dtype, rows, G, wdev, work, l.lwork_elems, info_dev, stream)) return 1;
   // memory row i of G = conj(eigenvector i) (column-major solver on the row-major array), ascending
   if (pdmrg_permute4(dtype, G + (size_t)E * (rows - 1) * rows, Ut, 1, 1, k, rows, 0, 0, -(long long)rows, 1, 1, nullptr, 0, stream)) return 1;
   if (pdmrg_permute4(dtype, a, mT, 1, 1, cols, rows, 0, 0, 1, cols, 0, nullptr, 0, stream)) return 1;   // mT[c,r] = a[r,c]
@@ -275,6 +302,8 @@ int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void
   // (zero-padded tensors right after a chi increase): hand the call to gesvd
   if (info_host != 0) return GRAM_FALLBACK;
   const double lam_top = lam[k - 1];
+  std::vector<double> lam_all(k);
+  for (int i = 0; i < k; ++i) lam_all[i] = lam[k - 1 - i];
   // ---- refinement of the small-singular-value tail: the Gram matrix of the projected rows
   //      U_tail^H a has norm (tau S_0)^2, so its eigen-decomposition resolves what level 0 cannot
   int t_prev = 0, nblk = k;       // current block = rows [t_prev, k), eigenvalues lam[0..nblk) ascending
@@ -289,7 +318,24 @@ int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void
     if (pdmrg_permute4(dtype, Ut + (size_t)E * t * rows, Uc, 1, 1, nt, rows, 0, 0, rows, 1, 1, nullptr, 0, stream)) return 1;
     if (pdmrg_gemm_nt(dtype, nt, cols, rows, 1, Uc, rows, 0, mT, rows, 0, 0, X2, cols, 0, 1.0, 0.0, 0, stream)) return 1;
     if (pdmrg_gemm_nt(dtype, nt, nt, cols, 1, X2, cols, 0, X2, cols, 0, 1, G2, nt, 0, 1.0, 0.0, 0, stream)) return 1;
-    if (heevd_inplace(s, dtype, nt, G2, wdev, work, l.lwork_elems, info_dev)) return 1;
+    // diag(G2)_i = |u_{t+i}^H a|^2 is an ACCURATE estimate of lambda_{t+i} (the level-0 eigenvalue carries noise
+    // eps*lambda_0).  Error model of the level-0 basis: direction i is off by min(S_i, eps S_0^2 / S_i); the second
+    // eigen-decomposition is skipped when the kept tail vectors [t, nkeep) cannot be wrong by more than 1e-9 S_0
+    // in total (product-like states with an empty tail, slowly decaying spectra).
+    {
+      std::vector<double> dg(nt);
+      PDMRG_CHECK_CUDA(cudaMemcpy2DAsync(dg.data(), 8, G2, (size_t)(nt + 1) * eb, 8, nt, cudaMemcpyDeviceToHost, stream));
+      PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));
+      const double eps_l0 = 2.2e-16 * lam_top;
+      double err2 = 0.0;
+      for (int i = 0; i < nkeep - t; ++i) {
+        const double li = dg[i] > 0.0 ? dg[i] : 0.0;
+        const double alt = li > 0.0 ? eps_l0 * eps_l0 / li : 0.0;
+        err2 += li < alt ? li : alt;
+      }
+      if (err2 <= 1e-18 * lam_top) break;
+    }
+    if (heevd_inplace(s, dtype, nt, G2, wdev, work, l.lwork_elems, info_dev, stream)) return 1;
     PDMRG_CHECK_CUDA(cudaMemcpyAsync(&info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
     PDMRG_CHECK_CUDA(cudaMemcpyAsync(lam.data(), wdev, (size_t)nt * 8, cudaMemcpyDeviceToHost, stream));
     PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -299,7 +345,14 @@ int svd_gram_wide(Solver* s, int dtype, int rows, int cols, int keep, const void
     if (pdmrg_permute4(dtype, Ut + (size_t)E * t * rows, Bt, 1, 1, rows, nt, 0, 0, 1, rows, 0, nullptr, 0, stream)) return 1;
     if (pdmrg_gemm_nt(dtype, nt, rows, nt, 1, W2, nt, 0, Bt, nt, 0, 0, Ut2, rows, 0, 1.0, 0.0, 0, stream)) return 1;
     PDMRG_CHECK_CUDA(cudaMemcpyAsync(Ut + (size_t)E * t * rows, Ut2, (size_t)nt * rows * eb, cudaMemcpyDeviceToDevice, stream));
+    for (int j = 0; j < nt; ++j) lam_all[t + j] = lam[nt - 1 - j];
     t_prev = t; nblk = nt;
+  }
+  if (basis_only) {
+    PDMRG_CHECK_CUDA(cudaMemcpyAsync(U, Ut, (size_t)k * rows * eb, cudaMemcpyDeviceToDevice, stream));
+    PDMRG_CHECK_CUDA(cudaMemcpyAsync(S, lam_all.data(), (size_t)k * 8, cudaMemcpyHostToDevice, stream));
+    PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));      // lam_all is a stack-owned host buffer
+    return 0;
   }
   // ---- Y = a^H U (column-major cols x k == row-major Yrow[a,c] = sum_r Ut[a,r] conj(mT[c,r])), Householder QR
   //      (only the nkeep leading columns: the discarded triplets are never formed)
@@ -461,6 +514,29 @@ extern "C" int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, 
   return 0;
 }
 
+extern "C" size_t pdmrg_left_basis_workspace_bytes(int dtype, int n, int c) {
+  Solver* s = get_solver();
+  if (!s) return 0;
+  GramLayout g;
+  if (gram_layout(s, dtype, n, c, &g)) return 0;
+  return g.total() + 256;
+}
+
+extern "C" int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X, void* Ut, double* lam, void* workspace,
+                                size_t workspace_bytes, int* info_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Solver* s = get_solver();
+  if (!s) return 1;
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_left_basis: bad dtype");
+  PDMRG_REQUIRE(n > 0 && c > 0, "pdmrg_left_basis: bad extents");
+  PDMRG_REQUIRE(workspace_bytes >= pdmrg_left_basis_workspace_bytes(dtype, n, c), "pdmrg_left_basis: workspace too small");
+  if (s->p_cusolverDnSetStream(s->handle, stream) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnSetStream failed"); return 1; }
+  const int rc = svd_gram_wide(s, dtype, n, c, keep, X, Ut, lam, nullptr, static_cast<unsigned char*>(workspace), info_dev,
+                               stream, true);
+  if (rc == GRAM_FALLBACK) { set_error("pdmrg_left_basis: cuSOLVER heevd did not converge"); return GRAM_FALLBACK; }
+  return rc;
+}
+
 extern "C" size_t pdmrg_heevd_workspace_bytes(int dtype, int n) {
   Solver* s = get_solver();
   if (!s) return 0;
@@ -481,6 +557,10 @@ extern "C" int pdmrg_heevd(int dtype, int n, void* a, double* w, void* workspace
   if (s->p_cusolverDnSetStream(s->handle, stream) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnSetStream failed"); return 1; }
   const int lwork = (int)(workspace_bytes / elem_bytes(dtype));
   cusolverStatus_t st;
+  // guard against underflowed diagonal entries (see shift_diag_kernel)
+  if (dtype == PDMRG_C128) shift_diag_kernel<true><<<1, 256, 0, stream>>>((double*)a, n, 1e-28);
+  else shift_diag_kernel<false><<<1, 256, 0, stream>>>((double*)a, n, 1e-28);
+  PDMRG_CHECK_LAUNCH();
   // row-major Hermitian a == column-major conj(a); its eigenvectors are the conjugates.
   if (dtype == PDMRG_C128) {
     st = s->p_cusolverDnZheevd(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, (cuDoubleComplex*)a, n, w,

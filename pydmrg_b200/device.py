@@ -293,6 +293,25 @@ def svd(a, workspace, method=SVD_GESVD, keep=0):
     return U, S, Vh, info
 
 
+def left_basis(X, workspace, keep=0):
+    """Refined left singular basis of X (n, c): returns (Ut (n,n) rows = u_a descending, lam (n,) = S^2,
+    info) or None when cuSOLVER's eigensolver did not converge."""
+    code = dtype_code(X)
+    n, c = X.shape
+    Ut = torch.empty((n, n), dtype=X.dtype, device=X.device)
+    lam = torch.empty(n, dtype=torch.float64, device=X.device)
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    nb = int(lib.pdmrg_left_basis_workspace_bytes(code, n, c))
+    if nb == 0:
+        check(1, "pdmrg_left_basis_workspace_bytes")
+    ws = workspace.get(nb)
+    rc = lib.pdmrg_left_basis(code, n, c, int(keep), _ptr(X), _ptr(Ut), _ptr(lam), _ptr(ws), ws.numel(), _ptr(info), _stream())
+    if rc == 77:
+        return None
+    check(rc, "pdmrg_left_basis")
+    return Ut, lam, info
+
+
 def heevd(a, workspace):
     """In-place Hermitian eigen-decomposition of a row-major (n,n) matrix; returns (w, a)
     with row i of ``a`` the i-th eigenvector (ascending)."""

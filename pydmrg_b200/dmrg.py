@@ -28,7 +28,7 @@ from .core import Context, default_context, is_dev, like
 from .eigs import calc_eigs
 from .env import calc_env, update_envL, update_envR
 from .mpo import mpo_conj_trans
-from .truncate import rdm_renormalize_left, rdm_renormalize_right, svd_truncate
+from .truncate import rdm_renormalize_left, rdm_renormalize_right, svd_truncate, truncate_twosite
 
 VERBOSE = 0
 
@@ -139,7 +139,7 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
                         stats=stats, return_device=True, **solver)
     tick.lap(stats, "t_eig")
     psi = v[:, 0].contiguous()
-    A, B, S, EE, EEs = svd_truncate(psi, (d1, d2, Dl, Dr), mbd, ctx, absorb=direction)
+    A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction)
     tick.lap(stats, "t_svd")
     mpsL[0][site] = like(A, proto)
     mpsL[0][site + 1] = like(B, proto)

@@ -56,6 +56,67 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     return A, B, Sn, EE, EEs
 
 
+def eig_truncate(psi, shape, mbd, ctx, direction):
+    """Projective two-site truncation for a MOVING centre (finite sweeps): only the isometry of the
+    side being left behind is needed, so ONE Hermitian eigen-decomposition of the reduced density
+    matrix replaces the SVD (same construction as the reference's one-site renormalizeR/L,
+    dmrg.py:49-136, applied to the two-site wave-function):
+
+      right:  rho = m m^H,  A = top-k eigenvectors (exact isometry),  new centre = A^H m  (= S Vh)
+      left :  rho = m^H m,  B = top-k eigenvectors^H,                 new centre = m B^H  (= U S)
+
+    with m[(Dl,d1),(d2,Dr)] = psi (mps_tools.py:105-107).  A (A^H m) is the exact projection of psi
+    on the kept subspace; Schmidt weights p_i = lambda_i / sum(lambda) are accurate to eps uniformly.
+    Returns A (d1,Dl,k), B (d2,k,Dr), S_normalised, EE, EEs like svd_truncate."""
+    d1, d2, Dl, Dr = shape
+    rows, cols = Dl * d1, d2 * Dr
+    k = min(int(mbd), rows, cols)
+    m = ctx.empty(rows, cols)
+    D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
+    mT = ctx.empty(cols, rows)
+    D.permute4(m, mT, (cols, rows), (1, cols))
+    X = m if direction == "right" else mT                       # left: eigenvectors of mT mT^H are conj(v_a)
+    n = X.shape[0]
+    res = D.left_basis(X, ctx.svd_ws, keep=k)
+    if res is None:                                             # cuSOLVER did not converge: LAPACK-grade route
+        return svd_truncate(psi, shape, mbd, Context_with(ctx, D.SVD_GESVD), absorb=direction)
+    Ut, lam_dev, info = res
+    lam = np.clip(lam_dev.cpu().numpy()[:k], 0.0, None)
+    EE, EEs, Sn = calc_entanglement(np.sqrt(lam))
+    A = ctx.empty(d1, Dl, k)
+    B = ctx.empty(d2, k, Dr)
+    if direction == "right":
+        # A[n,kl,a] = u_a[kl*d1+n];  centre C[a,c] = sum_x conj(u_a[x]) m[x,c]
+        D.permute4(Ut, A, (d1, Dl, k), (1, d1, n))
+        Vc = ctx.empty(k, rows)
+        D.permute4(Ut, Vc, (k, rows), (n, 1), conj=True)
+        C = D.gemm_nt(Vc, mT)
+        D.permute4(C, B, (d2, k, Dr), (Dr, cols, 1))
+    else:
+        # eigenvector rows w_a = conj(v_a):  B[q,a,s] = Vh[a,(q,s)] = w_a[(q,s)];  centre = m V = m conj(W)^T
+        D.permute4(Ut, B, (d2, k, Dr), (Dr, n, 1))
+        C = D.gemm_nt(m, Ut, M=rows, N=k, K=cols, lda=cols, ldb=n, ldc=k, conjB=True)      # (rows x k)
+        D.permute4(C, A, (d1, Dl, k), (k, d1 * k, 1))
+    return A, B, Sn, EE, EEs
+
+
+def Context_with(ctx, svd_method):
+    """Shallow view of a context with another SVD back-end (shares workspaces)."""
+    import copy
+    c = copy.copy(ctx)
+    c.svd_method = svd_method
+    return c
+
+
+def truncate_twosite(psi, shape, mbd, ctx, direction):
+    """Truncation used by the finite two-site sweep: projective (one heevd) for large cuts, full SVD
+    (cuSOLVER gesvd) for small ones or when an explicit SVD back-end was requested."""
+    d1, d2, Dl, Dr = shape
+    if ctx.svd_method < 0 and min(Dl * d1, d2 * Dr) >= 128:
+        return eig_truncate(psi, shape, mbd, ctx, direction)
+    return svd_truncate(psi, shape, mbd, ctx, absorb=direction)
+
+
 def renorm_inf(mpsList, mpoList, envList, vecs, mbd, ctx=None):
     """Drop-in for tools/mps_tools.py:98-120 (nStates handled state by state)."""
     ctx = ctx or default_context()

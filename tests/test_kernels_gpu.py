@@ -291,8 +291,29 @@ def test_svd_gram_decaying_spectrum(D, ws, real):
     torch.cuda.synchronize()
     U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
     assert info.item() == 0 and np.all(np.isfinite(U)) and np.all(np.isfinite(Vh))
-    assert rel((U * S) @ Vh, b) < 1e-11
+    # the refinement gate tolerates a level-0 error estimate of up to 1e-9 S_0 (csrc/solver.cu)
+    assert rel((U * S) @ Vh, b) < 2e-9
     assert np.allclose(Vh @ Vh.conj().T, np.eye(n), atol=1e-11) and np.allclose(U.conj().T @ U, np.eye(n), atol=1e-11)
+
+
+def test_svd_gram_zero_padded_regression(D, ws):
+    """A two-site wave-function captured right after a chi ramp (zero-padded tensors: 384 exactly-zero
+    columns, rows of norm ~1e-85): cuSOLVER's heevd does not converge on its raw Gram matrix; the
+    Gram route must still return finite, isometric factors (diagonal shift / gesvd fallback)."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "svd_rank_deficient.npz"))
+    a = np.zeros((512, 512), dtype=np.complex128)
+    a[:, f["cols"]] = f["block"]
+    for keep in (0, 256):
+        U, S, Vh, info = D.svd(dev(a.copy()), ws, D.SVD_GRAM, keep=keep)
+        torch.cuda.synchronize()
+        k = keep or 512
+        U, S, Vh = U.cpu().numpy()[:, :k], S.cpu().numpy()[:k], Vh.cpu().numpy()[:k]
+        assert info.item() == 0 and np.all(np.isfinite(U)) and np.all(np.isfinite(S)) and np.all(np.isfinite(Vh))
+        assert rel((U * S) @ Vh, a) < 1e-11
+        assert np.allclose(Vh @ Vh.conj().T, np.eye(k), atol=1e-11) and np.allclose(U.conj().T @ U, np.eye(k), atol=1e-11)
+        Sref = np.linalg.svd(a, compute_uv=False)
+        assert np.max(np.abs(S - Sref[:k])) < 1e-12 * Sref[0]
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])

@@ -280,3 +280,30 @@ def test_scan_driver_matches_independent_runs(P):
     assert r0["block"] == (0, 2) and r1["block"] == (2, 4)
     both = r0["E"] + r1["E"]
     assert np.allclose(both, one["E"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("direction", ["right", "left"])
+@pytest.mark.parametrize("dims", [(96, 80, 70), (128, 40, 60), (40, 128, 60)])
+def test_eig_truncate_projective(P, ctx, direction, dims):
+    """Projective truncation (one heevd): isometry exact, A.B reproduces the optimal rank-k
+    approximation of psi, Schmidt weights / EE match numpy's SVD to 1e-12."""
+    rng = np.random.default_rng(8)
+    d = 2
+    Dl, Dr, k = dims
+    r = min(Dl, Dr) * d
+    u, _ = np.linalg.qr(crand(rng, Dl * d, Dl * d)); v, _ = np.linalg.qr(crand(rng, d * Dr, d * Dr))
+    s = np.exp(-np.arange(r) * (25.0 / r))
+    m = (u[:, :r] * s) @ v.conj().T[:r]
+    psi = m.reshape(Dl, d, d, Dr).transpose(1, 2, 0, 3).copy()
+    A, B, S, EE, EEs = P.truncate.eig_truncate(ctx.dev(psi.reshape(-1)), (d, d, Dl, Dr), k, ctx, direction)
+    A, B = A.cpu().numpy(), B.cpu().numpy()
+    theta = np.einsum("nka,qas->nqks", A, B)
+    best = ((u[:, :k] * s[:k]) @ v.conj().T[:k]).reshape(Dl, d, d, Dr).transpose(1, 2, 0, 3)
+    assert np.linalg.norm(theta - best) < 1e-10 * np.linalg.norm(best)
+    if direction == "right":
+        assert np.allclose(np.einsum("nka,nkb->ab", A.conj(), A), np.eye(k), atol=1e-12)
+    else:
+        assert np.allclose(np.einsum("qas,qbs->ab", B, B.conj()), np.eye(k), atol=1e-12)
+    p = s[:k] ** 2 / np.sum(s[:k] ** 2)
+    assert abs(EE - np.sum(-p * np.log2(p))) < 1e-12
+    assert np.allclose(S ** 2, p, atol=1e-13)
