@@ -325,6 +325,7 @@ def main():
         line["sweep_sec"] = {"value": bs["ms_total"] * nb * 1e-3, "how": "derived: 198 bond steps x measured chi=%d "
                              "bond step (%d Davidson cycles); upper bound, edge bonds are smaller" % (chi, args.davidson_cycles)}
         line["cpu_baseline"] = cpu_baseline(args)
+        line["scan"] = scan_sample()
         if args.full_sweep:
             line["full_sweep"] = full_sweep(args, ctx)
     if rank == 0:
@@ -338,7 +339,7 @@ def bond_step(args, ctx, plan, L, R, W1, W2, chi):
     import torch
     from pydmrg_b200 import device as D
     from pydmrg_b200.davidson import davidson
-    from pydmrg_b200.truncate import svd_truncate
+    from pydmrg_b200.truncate import svd_truncate, truncate_twosite
     d = 2
     g = torch.Generator(device="cuda"); g.manual_seed(7)
     x0 = torch.randn(d * d * chi * chi, dtype=torch.complex128, device="cuda", generator=g)
@@ -355,13 +356,14 @@ def bond_step(args, ctx, plan, L, R, W1, W2, chi):
         _, vecs = davidson(lambda xx, yy: plan.apply(xx, yy, -1.0), [x0], plan.n, D.C128, ctx.device, nroots=1,
                            fixed_cycles=args.davidson_cycles, stats=stats)
         b.record()
-        A, B, S, EE, EEs = svd_truncate(vecs[0], (d, d, chi, chi), chi, ctx, absorb="right")
+        A, B, S, EE, EEs = truncate_twosite(vecs[0], (d, d, chi, chi), chi, ctx, "right")   # the sweep's truncation
         c.record()
         newL = D.env_update_right(A, W1.astype(np.complex128), L, None, ctx.ws)
         e.record()
         torch.cuda.synchronize()
         out = {"davidson_ms": a.elapsed_time(b), "n_matvec": stats["n_matvec"], "svd_truncate_ms": b.elapsed_time(c),
-               "env_update_ms": c.elapsed_time(e), "ms_total": a.elapsed_time(e), "svd": args.svd}
+               "env_update_ms": c.elapsed_time(e), "ms_total": a.elapsed_time(e),
+               "truncation": "projective (pdmrg_left_basis: Gram GEMM + heevd, gated tail refinement)" if args.svd == "auto" else args.svd}
     if ctx_ref is not None:
         a, b = ev(), ev()
         svd_truncate(vecs[0], (d, d, chi, chi), chi, ctx_ref, absorb="right")
@@ -398,6 +400,23 @@ def cpu_baseline(args):
                       % (chi_a, n),
             "blas_fair": {"value": heff2_flops(chi_b) / tb * 1e-9, "unit": "GFLOP/s", "cores": os.cpu_count(),
                           "sample": "same contractions via np.tensordot (threaded zgemm) at chi=%d, 1 call" % chi_b}}
+
+
+def scan_sample():
+    """s-points/hour on one GPU from a bounded sample of BASELINE configs[3] (ASEP N=50, chi=256 two-site,
+    s in [-0.5, 0.5]): two scan points, each cold-started through a [16, 64] chi ramp."""
+    import torch
+    from pydmrg_b200 import mpo as M, scan
+    s_vals = np.linspace(-0.5, 0.5, 64)[:2]
+    mpo_of = lambda s: M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    np.random.seed(0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = scan.run_scan(mpo_of, s_vals, 256, maxIter=3, tol=1e-8)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    per = float(np.mean(res["sec"]))
+    return {"config": "ASEP N=50 chi=256 two-site, 2 of 64 s-points, each cold through a [16,64] chi ramp, tol 1e-8",
+            "sec_per_point": res["sec"], "s_points_per_hour_per_gpu": 3600.0 / per,
+            "E": [float(np.real(e)) for e in res["E"]], "E_imag_max": float(np.max(np.abs(np.imag(res["E"]))))}
 
 
 def full_sweep(args, ctx):

@@ -41,8 +41,9 @@ def _site_ops(M, W, F, site, oneSite, ctx):
             # [L, R] (tools/env_tools.py:74-75) is addressed as F[site+1] by the reference
             R = ctx.dev(F[m][site + 2] if len(F[m]) > site + 2 else F[m][site + 1])
             W1, W2 = W[m][site], W[m][site + 1]
-            if W1 is None and W2 is None:
-                continue                                         # diag_tools.py:150-151
+            # None = identity passing the MPO bond through, as in the one-site code
+            # (diag_tools.py:113-115).  The reference's two-site Hfun skips such terms (:150-151,
+            # "Adapt to No operator"), which drops wrap-around strings; here they are applied.
             if W1 is None:
                 W1 = np.einsum("ab,ij->abij", np.eye(L.shape[1]), np.eye(shape[0]))
             if W2 is None:

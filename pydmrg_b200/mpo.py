@@ -36,9 +36,11 @@ def _assemble(N, w, site_entries):
     return [ops]
 
 
-def asep_mpo(N, params):
+def asep_mpo(N, params, periodic=False):
     """Open-boundary ASEP tilted generator, params = (alpha, gamma, p, q, beta, delta, s)
-    (scalars; alpha/gamma act on site 0, beta/delta on site N-1).  w = 6."""
+    (scalars; alpha/gamma act on site 0, beta/delta on site N-1).  w = 6.
+    ``periodic=True`` appends the reference's wrap-around terms as extra w = 1 operators with
+    ``None`` (identity) entries in between (mpo/asep.py:70-94)."""
     a, g, p, q, b, d, s = [float(t) for t in params]
     O = _OPS
     es, ems = np.exp(s), np.exp(-s)
@@ -54,7 +56,20 @@ def asep_mpo(N, params):
                 (3, 0): q * ems * O["Sp"], (4, 0): q * O["n"], (5, 0): corner,
                 (5, 1): O["Sp"], (5, 2): -O["n"], (5, 3): O["Sm"], (5, 4): -O["v"], (5, 5): O["I"]}
 
-    return _assemble(N, 6, entries)
+    mpoL = _assemble(N, 6, entries)
+    if periodic:
+        def string(first, last):
+            op = [None] * N
+            op[0] = first.reshape(1, 1, 2, 2).copy()
+            op[-1] = last.reshape(1, 1, 2, 2).copy()
+            return op
+        if p != 0:
+            mpoL.append(string(O["Sm"], p * es * O["Sp"]))
+            mpoL.append(string(O["v"], -p * O["n"]))
+        if q != 0:
+            mpoL.append(string(O["Sp"], q * ems * O["Sm"]))
+            mpoL.append(string(O["n"], -q * O["v"]))
+    return mpoL
 
 
 def tasep_mpo(N, alpha, beta, s):

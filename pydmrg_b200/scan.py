@@ -17,8 +17,15 @@ from .parallel import gather_scan, scan_block
 
 
 def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
-             twoSite=True, dtype="c128", continuation=True, stats=None, **solver):
+             twoSite=True, dtype="c128", continuation=False, ramp_res_tol=1e-5, stats=None, **solver):
     """Run ``run_dmrg(mpo_of(v), mbd=...)`` for every v in ``values`` (this rank's block only).
+
+    Every point cold-starts through the chi ramp by default: the ramp stages run one sweep with a
+    loose Davidson residual (``ramp_res_tol``), the target chi runs to ``tol`` with the solver's
+    normal stopping rule.  ``continuation=True`` warm-starts a point from the previous point of the
+    block, as the reference's scripts do -- with two-site sweeps of a single (right) eigenvector the
+    Ritz value can leave the Perron branch of these non-Hermitian generators after a warm start
+    (observed at N=50, chi=256), so it is opt-in.
 
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
     rank's points, block: (lo, hi))."""
@@ -33,11 +40,14 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
         if prev is None or not continuation:
             # cold start: chi ramp with in-memory continuation between stages
             guess = None
-            for chi in list(ramp) + [mbd]:
-                if chi > mbd:
-                    continue
-                out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if chi == mbd else 1, minIter=minIter,
-                               initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **solver)
+            stages = [c for c in ramp if c < mbd] + [mbd]
+            for chi in stages:
+                last = chi == mbd
+                opts = dict(solver)
+                if not last and ramp_res_tol is not None:
+                    opts["res_tol"] = ramp_res_tol
+                out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
+                               initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **opts)
                 guess = _grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd]))
         else:
             out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,

@@ -37,6 +37,12 @@ def test_mpo_builders_equal_reference(ref, prm, N):
     b = mine.asep_curr_mpo(N, prm)
     for Wa, Wb in zip(a[0], b[0]):
         assert Wa.shape == Wb.shape and np.array_equal(Wa, Wb)
+    ap = ref.asep.return_mpo(N, prm, periodic=True)
+    bp = mine.asep_mpo(N, prm, periodic=True)
+    assert len(ap) == len(bp)
+    for opa, opb in zip(ap, bp):
+        for Wa, Wb in zip(opa, opb):
+            assert (Wa is None and Wb is None) or np.array_equal(Wa, Wb)
     with quiet():
         ct = ref.mpo_tools.mpo_conj_trans(ref.asep.return_mpo(N, prm))
     for Wa, Wb in zip(ct[0], mine.mpo_conj_trans(mine.asep_mpo(N, prm))[0]):

@@ -252,13 +252,13 @@ def test_heisenberg_f64_two_site(P):
 
 
 def test_scan_driver_matches_independent_runs(P):
-    """s-scan: block continuation gives the same energies as independent cold runs, and
-    the two-block (2-rank) decomposition reproduces the one-block result."""
+    """s-scan: block continuation and cold starts both reproduce dense ED, and the
+    two-block (2-rank) decomposition reproduces the one-block result."""
     from pydmrg_b200 import scan
     s_vals = np.linspace(-0.4, 0.2, 4)
     mpo_of = lambda s: P.mpo.asep_mpo(8, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
     np.random.seed(0)
-    one = scan.run_scan(mpo_of, s_vals, 16, ramp=(4,), tol=1e-11, maxIter=6, res_tol=1e-11)
+    one = scan.run_scan(mpo_of, s_vals, 16, ramp=(4,), tol=1e-11, maxIter=6, res_tol=1e-11, continuation=True)
     assert one["block"] == (0, 4) and one["E"].shape == (4,)
     # reference values: dense ED of each point
     from oracle import dmrg_oracle as orc
@@ -307,3 +307,76 @@ def test_eig_truncate_projective(P, ctx, direction, dims):
     p = s[:k] ** 2 / np.sum(s[:k] ** 2)
     assert abs(EE - np.sum(-p * np.log2(p))) < 1e-12
     assert np.allclose(S ** 2, p, atol=1e-13)
+
+
+def test_two_states_gap(P):
+    """nStates=2 (SURVEY 8f.3): block Davidson with two roots, state-averaged RDM (dmrg.py:56-66);
+    E and the gap E0-E1 against dense ED (the reference's davidsonMultipleCheck compares at 1e-4)."""
+    prm = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)
+    N = 6
+    mpo = P.mpo.asep_mpo(N, prm)
+    T = mpo[0][0][0]
+    for W in mpo[0][1:]:
+        T = np.einsum("a...,abij->b...ij", T, W)
+    T = T[0]
+    idx = list(range(0, 2 * N, 2)) + list(range(1, 2 * N, 2))
+    ev = np.linalg.eigvals(T.transpose(idx).reshape(2 ** N, 2 ** N))
+    ev = ev[np.argsort(-ev.real)]
+    np.random.seed(6)
+    out = P.dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=6, nStates=2, res_tol=1e-10)
+    E, EE, gap = out[0], out[1], out[2]
+    assert abs(E - ev[0]) < 1e-7 * abs(ev[0])
+    assert abs(gap - (ev[0] - ev[1])) < 1e-6 * abs(ev[0])
+
+
+def _dense_from_mpo(mpoL, N, d=2):
+    H = 0
+    for op in mpoL:
+        T = None
+        for W in op:
+            Wm = np.eye(d).reshape(1, 1, d, d) if W is None else W
+            if T is None:
+                T = Wm[0]
+            else:
+                if Wm.shape[0] == 1 and T.shape[0] != 1:
+                    Wm = np.einsum("ab,ij->abij", np.eye(T.shape[0]), Wm[0, 0])
+                T = np.einsum("a...,abij->b...ij", T, Wm)
+        T = T[0]
+        idx = list(range(0, 2 * N, 2)) + list(range(1, 2 * N, 2))
+        H = H + T.transpose(idx).reshape(d ** N, d ** N)
+    return H
+
+
+def test_periodic_mpo_with_none_entries(P):
+    """Several MPO terms, ``None`` (identity) entries between the ends of the wrap-around strings
+    (mpo/asep.py:70-94; tools/diag_tools.py:113-115, tools/env_tools.py:31-33): one-site and two-site
+    DMRG against dense ED of the periodic generator (the reference's periodicCheck idea)."""
+    prm = (0.0, 0.0, 0.3, 0.7, 0.0, 0.0, -0.3)
+    N = 6
+    mpo = P.mpo.asep_mpo(N, prm, periodic=True)
+    assert len(mpo) == 5 and mpo[1][2] is None
+    # dense H: main operator + strings (identity in between carries the w = 1 bond)
+    H = _dense_from_mpo(mpo, N)
+    ev = np.linalg.eigvals(H)
+    top = ev[np.argmax(ev.real)]
+    np.random.seed(5)
+    out = P.dmrg.run_dmrg(mpo, mbd=8, tol=1e-11, maxIter=8, res_tol=1e-11)
+    assert abs(out[0] - top) < 1e-8 * max(1.0, abs(top))
+    np.random.seed(5)
+    out2 = P.dmrg.run_dmrg(mpo, mbd=8, tol=1e-11, maxIter=6, res_tol=1e-11, twoSite=True)
+    assert abs(out2[0] - top) < 1e-8 * max(1.0, abs(top))
+
+
+def test_odd_bond_dimension_f64(P):
+    """Ragged / odd bond dimensions in real arithmetic exercise the non-TMA GEMM path (row strides
+    that are not 16-byte multiples) inside a whole run: Heisenberg N=7, chi=5."""
+    N = 7
+    mpo = P.mpo.heisenberg_mpo(N)
+    top = np.max(np.linalg.eigvalsh(_dense_from_mpo(mpo, N)))
+    np.random.seed(3)
+    stats = {}
+    out = P.dmrg.run_dmrg(mpo, mbd=[3, 5, 8], tol=1e-12, maxIter=6, res_tol=1e-11, dtype="f64", twoSite=True, stats=stats)
+    E = out[0]
+    assert E.shape == (3,)
+    assert abs(E[2] - top) < 1e-9 * abs(top)         # chi = 8 is exact for N = 7
+    assert E[0].real <= E[1].real + 1e-12 <= E[2].real + 2e-12   # variational in chi for the symmetric problem
