@@ -106,6 +106,38 @@ int pdmrg_heff_apply_timed(pdmrg_heff_plan* plan, const void* const* L_host_ptrs
 int pdmrg_heff_plan_create_sharded(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
                                    const int* wL_host, const int* wR_host, const void* const* Wc_host,
                                    const unsigned char* const* block_mask_host);
+/* ---- bond-sharded mat-vec with the exchange fused into the kernels -----------------
+ * One process per GPU.  Each rank allocates three buffers with pdmrg_ipc_alloc (slab buffer Z,
+ * y staging buffer, flag array of 2*world uint64), ships the 64-byte handles to its peers through
+ * any host channel (torch.distributed / MPI), opens the peers' handles and builds a communicator.
+ * pdmrg_heff_apply_fused then runs stage A and the W mix locally, stage C with a SCATTER epilogue
+ * that stores every output tile straight into the memory of the rank owning those rows of y
+ * (peer st.global over NVLink), and a reduce + all-gather-by-peer-stores kernel guarded by
+ * system-scope flags; every rank ends with a bit-identical y.  No NCCL call on this path.
+ * jmask_all_ranks[r] = bit mask of the MPO-bond slabs j rank r produces (pdmrg_heff_needed_j). */
+typedef struct pdmrg_comm pdmrg_comm;
+int pdmrg_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int pdmrg_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int pdmrg_ipc_close(void* dev_ptr);
+int pdmrg_ipc_free(void* dev_ptr);
+int pdmrg_comm_create(pdmrg_comm** comm, int rank, int world, void* const* Zpeer, void* const* Ypeer,
+                      void* const* Fpeer);
+void pdmrg_comm_destroy(pdmrg_comm* comm);
+size_t pdmrg_comm_z_bytes(const pdmrg_heff_plan* plan, int world);
+size_t pdmrg_comm_y_bytes(const pdmrg_heff_plan* plan);
+int pdmrg_heff_needed_j(const pdmrg_heff_plan* plan, int mpo, unsigned int* mask_out);
+int pdmrg_heff_apply_fused(pdmrg_heff_plan* plan, pdmrg_comm* comm, const void* const* L_host_ptrs,
+                           const void* const* R_host_ptrs, const void* x, void* y, double sign,
+                           const unsigned int* jmask_all_ranks, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* the GEMM with the scatter epilogue on its own: rows [q*rows_per_owner, ...) of C go to Cpeer_host[q] */
+int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                          const void* A, long long lda, long long strideA1, long long strideA2,
+                          const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                          const void* const* Cpeer_host, int n_owner, int rows_per_owner,
+                          long long ldc, long long strideC1, long long strideC2,
+                          double alpha_re, double alpha_im, void* stream);
+
 /* algorithmic FLOPs of one apply (dense-W count of SURVEY 8d) and with block sparsity */
 double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan);
 double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan);

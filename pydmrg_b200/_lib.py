@@ -44,6 +44,17 @@ def _load():
         "pdmrg_heff_workspace_bytes": (sz, [vp]),
         "pdmrg_heff_apply": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp]),
         "pdmrg_heff_apply_timed": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp, POINTER(ctypes.c_float)]),
+        "pdmrg_ipc_alloc": (i, [sz, POINTER(vp), ctypes.c_char_p]),
+        "pdmrg_ipc_open": (i, [ctypes.c_char_p, POINTER(vp)]),
+        "pdmrg_ipc_close": (i, [vp]),
+        "pdmrg_ipc_free": (i, [vp]),
+        "pdmrg_comm_create": (i, [POINTER(vp), i, i, POINTER(vp), POINTER(vp), POINTER(vp)]),
+        "pdmrg_comm_destroy": (None, [vp]),
+        "pdmrg_comm_z_bytes": (sz, [vp, i]),
+        "pdmrg_comm_y_bytes": (sz, [vp]),
+        "pdmrg_heff_needed_j": (i, [vp, i, POINTER(ctypes.c_uint)]),
+        "pdmrg_heff_apply_fused": (i, [vp, vp, POINTER(vp), POINTER(vp), vp, vp, d, POINTER(ctypes.c_uint), vp, sz, vp]),
+        "pdmrg_gemm_nt_scatter": (i, [i, i, i, i, i, i, POINTER(i), vp, ll, ll, ll, vp, ll, ll, ll, i, POINTER(vp), i, i, ll, ll, ll, d, d, vp]),
         "pdmrg_heff_flops_dense": (d, [vp]),
         "pdmrg_heff_flops_sparse": (d, [vp]),
         "pdmrg_heff_flops_gemm": (d, [vp]),

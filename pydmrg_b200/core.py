@@ -37,6 +37,7 @@ class Context:
         if not torch.cuda.is_available():
             raise RuntimeError("pydmrg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        D.set_device_index(self.device.index if self.device.index is not None else torch.cuda.current_device())
         self.tdtype = D.torch_dtype(self.code)
         self.npdtype = D.np_dtype(self.code)
         self.ws = D.Workspace(self.device)

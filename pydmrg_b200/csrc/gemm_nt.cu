@@ -47,6 +47,11 @@ struct GemmParams {
   int beta, conjB;
   int bcastA1, bcastA2, bcastB1, bcastB2;
   int idx2[MAX_IDX2];
+  // SCATTER epilogue: rows [q*rows_per_owner, (q+1)*rows_per_owner) of C go to Cpeer[q] (a peer GPU's
+  // memory mapped through CUDA IPC) -- the reduce-scatter of a bond-sharded mat-vec rides on the
+  // GEMM epilogue, tile by tile, as plain st.global over NVLink
+  double* Cpeer[8];
+  int rows_per_owner;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -86,7 +91,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <bool CPLX, int MI>
+template <bool CPLX, int MI, bool SCATTER = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -206,7 +211,8 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     // ------------------------------ epilogue ----------------------------------------
-    double* Cb = p.C + (CPLX ? 2 : 1) * ((long long)(b / p.nb2) * p.strideC1 + (long long)p.idx2[b % p.nb2] * p.strideC2);
+    const long long boff = (CPLX ? 2 : 1) * ((long long)(b / p.nb2) * p.strideC1 + (long long)p.idx2[b % p.nb2] * p.strideC2);
+    double* Cb = p.C + boff;
     const int row0 = tm * BM + wm * (8 * MI) + permg;
     if (CPLX) {
       const int col0 = tn * (BNR / 2) + wn * 16;
@@ -214,11 +220,18 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = 0; i < MI; ++i) {
         const int row = row0 + i * 8;
         if (row >= p.M) continue;
+        double* Crow;
+        if (SCATTER) {
+          const int owner = row / p.rows_per_owner;
+          Crow = p.Cpeer[owner] + boff + 2 * (long long)(row - owner * p.rows_per_owner) * p.ldc;
+        } else {
+          Crow = Cb + 2 * (long long)row * p.ldc;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = col0 + t * 2 + (j & 1) + (j >> 1) * 8;
           if (col >= p.N) continue;
-          double2* dst = reinterpret_cast<double2*>(Cb + 2 * ((long long)row * p.ldc + col));
+          double2* dst = reinterpret_cast<double2*>(Crow + 2 * col);
           const double re = acc[i][j][0], im = acc[i][j][1];
           double2 out = make_double2(p.alpha_re * re - p.alpha_im * im, p.alpha_re * im + p.alpha_im * re);
           if (p.beta) { const double2 old = *dst; out.x += old.x; out.y += old.y; }
@@ -233,9 +246,16 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = 0; i < MI; ++i) {
         const int row = row0 + i * 8;
         if (row >= p.M) continue;
+        double* Crow;
+        if (SCATTER) {
+          const int owner = row / p.rows_per_owner;
+          Crow = p.Cpeer[owner] + boff + (long long)(row - owner * p.rows_per_owner) * p.ldc;
+        } else {
+          Crow = Cb + (long long)row * p.ldc;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          double* dst = Cb + (long long)row * p.ldc + col0 + j * 8;
+          double* dst = Crow + col0 + j * 8;
           if (col0 + j * 8 + pc0 < p.N) {
             double v = p.alpha_re * acc[i][j][0];
             if (p.beta) v += dst[pc0];
@@ -377,11 +397,41 @@ extern "C" int pdmrg_last_gemm_path(void) { return g_last_path.load(); }
 extern "C" void pdmrg_set_force_generic_gemm(int on) { g_force_generic.store(on); }
 extern "C" void pdmrg_set_force_tile_rows(int bm) { g_force_bm.store(bm); }
 
+static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                        const void* A, long long lda, long long strideA1, long long strideA2,
+                        const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                        void* C, long long ldc, long long strideC1, long long strideC2,
+                        double alpha_re, double alpha_im, int beta, void* stream_,
+                        const void* const* Cpeer, int n_owner, int rows_per_owner);
+
 extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
                                       const void* A, long long lda, long long strideA1, long long strideA2,
                                       const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
                                       void* C, long long ldc, long long strideC1, long long strideC2,
                                       double alpha_re, double alpha_im, int beta, void* stream_) {
+  return gemm_nt_impl(dtype, M, N, K, nb1, nb2, idx2_host, A, lda, strideA1, strideA2, B, ldb, strideB1, strideB2, conjB, C, ldc,
+                      strideC1, strideC2, alpha_re, alpha_im, beta, stream_, nullptr, 0, 0);
+}
+
+extern "C" int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                                     const void* A, long long lda, long long strideA1, long long strideA2,
+                                     const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                                     const void* const* Cpeer_host, int n_owner, int rows_per_owner,
+                                     long long ldc, long long strideC1, long long strideC2,
+                                     double alpha_re, double alpha_im, void* stream_) {
+  PDMRG_REQUIRE(n_owner >= 1 && n_owner <= 8 && rows_per_owner > 0, "pdmrg_gemm_nt_scatter: bad owner layout");
+  PDMRG_REQUIRE((long long)n_owner * rows_per_owner >= M, "pdmrg_gemm_nt_scatter: owners do not cover the rows");
+  return gemm_nt_impl(dtype, M, N, K, nb1, nb2, idx2_host, A, lda, strideA1, strideA2, B, ldb, strideB1, strideB2, conjB,
+                      const_cast<void*>(Cpeer_host[0]), ldc, strideC1, strideC2, alpha_re, alpha_im, 0, stream_, Cpeer_host, n_owner,
+                      rows_per_owner);
+}
+
+static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                        const void* A, long long lda, long long strideA1, long long strideA2,
+                        const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                        void* C, long long ldc, long long strideC1, long long strideC2,
+                        double alpha_re, double alpha_im, int beta, void* stream_,
+                        const void* const* Cpeer, int n_owner, int rows_per_owner) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_gemm_nt: bad dtype");
   PDMRG_REQUIRE(beta == 0 || beta == 1, "pdmrg_gemm_nt: beta must be 0 or 1");
@@ -417,6 +467,10 @@ extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, i
   p.beta = beta; p.conjB = conjB;
   p.bcastA1 = (strideA1 == 0 || nb1 == 1); p.bcastA2 = (strideA2 == 0 || max2 == 0);
   p.bcastB1 = (strideB1 == 0 || nb1 == 1); p.bcastB2 = (strideB2 == 0 || max2 == 0);
+  for (int i = 0; i < 8; ++i) p.Cpeer[i] = (Cpeer && i < n_owner) ? static_cast<double*>(const_cast<void*>(Cpeer[i])) : nullptr;
+  p.rows_per_owner = rows_per_owner > 0 ? rows_per_owner : 1;
+  const bool scatter = Cpeer != nullptr;
+  if (scatter) PDMRG_REQUIRE(beta == 0, "pdmrg_gemm_nt_scatter: beta must be 0");
 
   if (use_tma) {
     static bool attr_set = false;
@@ -439,7 +493,23 @@ extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, i
     const long long total = (long long)p.tiles_m * p.tiles_n * nbatch;
     PDMRG_REQUIRE(total < (1ll << 31), "pdmrg_gemm_nt: too many tiles");
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    if (bm == 128) {
+    if (scatter) {
+      static bool attr2 = false;
+      if (!attr2) {
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr2 = true;
+      }
+      if (bm == 128) {
+        if (cplx) gemm_nt_dmma_kernel<true, 8, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+        else gemm_nt_dmma_kernel<false, 8, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+      } else {
+        if (cplx) gemm_nt_dmma_kernel<true, 4, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+        else gemm_nt_dmma_kernel<false, 4, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+      }
+    } else if (bm == 128) {
       if (cplx) gemm_nt_dmma_kernel<true, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
       else gemm_nt_dmma_kernel<false, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
     } else {
@@ -452,6 +522,7 @@ extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, i
     return 0;
   }
 
+  PDMRG_REQUIRE(!scatter, "pdmrg_gemm_nt_scatter: operands must be TMA-compatible (16-byte aligned, even strides)");
   dim3 grid((N + 31) / 32, (M + 31) / 32, (unsigned)nbatch);
   PDMRG_REQUIRE(grid.y <= 65535 && nbatch <= 65535, "pdmrg_gemm_nt: generic path extent too large");
   p.kiters = 0; p.tiles_m = p.tiles_n = 0;

@@ -17,6 +17,13 @@
 
 using namespace pdmrg;
 
+extern "C" int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
+                                     const void* A, long long lda, long long strideA1, long long strideA2,
+                                     const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
+                                     const void* const* Cpeer_host, int n_owner, int rows_per_owner,
+                                     long long ldc, long long strideC1, long long strideC2,
+                                     double alpha_re, double alpha_im, void* stream_);
+
 struct pdmrg_heff_plan {
   int dtype, P, Dl, Dr, n_mpo;
   std::vector<int> wL, wR;
@@ -235,6 +242,73 @@ int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* cons
   return 0;
 }
 }  // namespace
+
+// ---------------------------------------------------------------------------------------
+// Bond-sharded mat-vec with the exchange fused into the kernels (peer memory, no NCCL)
+// ---------------------------------------------------------------------------------------
+extern "C" size_t pdmrg_comm_z_bytes(const pdmrg_heff_plan* pl, int world) {
+  if (!pl) return 0;
+  const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
+  const int chunk = (pl->Dl + world - 1) / world;
+  int wl = 1;
+  for (int v : pl->wL) if (v > wl) wl = v;
+  return (size_t)world * pl->P * wl * chunk * pl->Dr * 8 * E + 256;
+}
+
+extern "C" size_t pdmrg_comm_y_bytes(const pdmrg_heff_plan* pl) {
+  if (!pl) return 0;
+  return (size_t)pl->P * pl->Dl * pl->Dr * elem_bytes(pl->dtype) + 256;
+}
+
+extern "C" int pdmrg_heff_needed_j(const pdmrg_heff_plan* pl, int mpo, unsigned int* mask_out) {
+  PDMRG_REQUIRE(pl && mpo >= 0 && mpo < pl->n_mpo, "pdmrg_heff_needed_j: bad arguments");
+  unsigned int m = 0;
+  for (int j = 0; j < pl->wL[mpo] && j < 32; ++j) if (pl->need_j[mpo][j]) m |= 1u << j;
+  *mask_out = m;
+  return 0;
+}
+
+extern "C" int pdmrg_heff_apply_fused(pdmrg_heff_plan* pl, pdmrg_comm* comm, const void* const* Ls, const void* const* Rs,
+                                      const void* x, void* y, double sign, const unsigned int* jmask_all_ranks,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(pl && comm, "pdmrg_heff_apply_fused: null plan / communicator");
+  PDMRG_REQUIRE(pl->n_mpo == 1, "pdmrg_heff_apply_fused: one MPO term per plan");
+  PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply_fused: workspace too small");
+  const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
+  const int P = pl->P, Dl = pl->Dl, Dr = pl->Dr, wl = pl->wL[0], wr = pl->wR[0];
+  const int world = comm_world(comm), rank = comm_rank(comm);
+  const int chunk = (Dl + world - 1) / world;
+  const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl;
+  double* T = static_cast<double*>(workspace);
+  double* U = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align_up(t_elems * 8 * E, 256));
+  std::vector<int> olist, jlist;
+  for (int o = 0; o < wr; ++o) if (pl->need_o[0][o]) olist.push_back(o);
+  for (int j = 0; j < wl; ++j) if (pl->need_j[0][j]) jlist.push_back(j);
+  PDMRG_REQUIRE(olist.size() <= 32 && jlist.size() <= 32 && wl <= 32, "pdmrg_heff_apply_fused: MPO bond above 32");
+  comm_next_epoch(comm);
+  if (!olist.empty() && !jlist.empty()) {
+    const double* R = static_cast<const double*>(Rs[0]);
+    const double* L = static_cast<const double*>(Ls[0]);
+    if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, P * Dl, Dr, 1, (int)olist.size(), olist.data(), R, (long long)wr * Dr, 0, Dr,
+                               x, Dr, 0, 0, 0, T, (long long)wr * P * Dl, 0, (long long)P * Dl, 1.0, 0.0, 0, stream))
+      return 1;
+    if (launch_mix(pl->dtype, pl->mix[0], T, U, Dr, Dl, (long long)wr * P * Dl, 1, (long long)wl * Dl, 1, stream)) return 1;
+    // stage C with the SCATTER epilogue: rows [q*chunk, (q+1)*chunk) of every (pout, j) slab are stored
+    // into rank q's Z buffer at [src = this rank][pout][j][il][r]
+    const void* Cpeer[8];
+    for (int q = 0; q < world; ++q) Cpeer[q] = comm_zpeer(comm, q) + (size_t)E * rank * P * wl * chunk * Dr;
+    if (pdmrg_gemm_nt_scatter(pl->dtype, Dl, Dr, Dl, P, (int)jlist.size(), jlist.data(), L, (long long)wl * Dl, 0, Dl,
+                              U, (long long)wl * Dl, (long long)Dr * wl * Dl, Dl, 0, Cpeer, world, chunk, Dr,
+                              (long long)wl * chunk * Dr, (long long)chunk * Dr, 1.0, 0.0, stream))
+      return 1;
+  }
+  if (comm_signal(comm, 0, stream)) return 1;
+  if (comm_reduce_gather(comm, jmask_all_ranks, P, wl, chunk, Dl, Dr, E, sign, stream)) return 1;
+  if (comm_signal(comm, 1, stream)) return 1;
+  if (comm_wait_copy(comm, y, (long long)P * Dl * Dr * E, stream)) return 1;
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // Environment updates

@@ -40,3 +40,16 @@ int launch_reduce_slabs(int dtype, const void* Z, void* y, long long n_elems, in
                         long long zstride_b, long long zstride_q, double sign, int accumulate, cudaStream_t stream);
 
 }  // namespace pdmrg
+
+// peer-memory communicator of the bond-sharded mat-vec (comm.cu)
+struct pdmrg_comm;
+namespace pdmrg {
+int comm_signal(pdmrg_comm* c, int phase, cudaStream_t stream);
+int comm_reduce_gather(pdmrg_comm* c, const unsigned int* jmask, int P, int wl, int chunk, int Dl, int Dr, int E, double sign,
+                       cudaStream_t stream);
+int comm_wait_copy(pdmrg_comm* c, void* y, long long n_doubles, cudaStream_t stream);
+int comm_rank(const pdmrg_comm* c);
+int comm_world(const pdmrg_comm* c);
+void comm_next_epoch(pdmrg_comm* c);
+double* comm_zpeer(const pdmrg_comm* c, int q);
+}  // namespace pdmrg

@@ -13,8 +13,25 @@ from . import _lib
 from ._lib import C128, F64, check, lib
 
 
+_DEV_INDEX = None
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw cudaStream_t of torch's current stream (the fast private accessor: this is called once
+    per kernel launch and torch.cuda.current_stream() costs ~15 us)."""
+    global _DEV_INDEX
+    if _DEV_INDEX is None:
+        _DEV_INDEX = torch.cuda.current_device()
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(_DEV_INDEX))
+    except AttributeError:          # private API moved: fall back to the public one
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def set_device_index(index):
+    """Call after torch.cuda.set_device() if the device changes within a process."""
+    global _DEV_INDEX
+    _DEV_INDEX = int(index)
 
 
 def _ptr(t):

@@ -108,3 +108,87 @@ class ShardedHeff:
         if self.world > 1:
             self.dist.all_reduce(torch.view_as_real(y) if y.is_complex() else y, op=self.dist.ReduceOp.SUM)
         return y
+
+
+class FusedShardedHeff:
+    """MPO-bond-sharded mat-vec whose exchange is done by the kernels themselves over peer memory
+    (CUDA IPC + NVLink loads/stores): stage-C GEMM with a scatter epilogue -> flag -> reduce + all-gather
+    by peer stores -> flag -> copy.  No NCCL on the data path; ``dist`` is only used once, to ship the
+    64-byte IPC handles and the slab masks between the ranks.  world == 1 runs the same kernels on
+    the local buffers."""
+
+    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist=None):
+        import ctypes
+        import torch
+        from . import device as D
+        from ._lib import check, lib
+        assert len(ops) == 1, "one MPO term per fused plan"
+        self.rank, self.world = rank, world
+        L, Wc, R = ops[0]
+        pat = block_pattern(Wc, L.shape[1], R.shape[1], P)
+        self.partition = [partition_blocks(pat, world)]
+        self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, block_masks=[self.partition[0][rank]])
+        self.n = self.plan.n
+        self._lib, self._check, self._ct = lib, check, ctypes
+        sizes = [int(lib.pdmrg_comm_z_bytes(self.plan._plan, world)), int(lib.pdmrg_comm_y_bytes(self.plan._plan)),
+                 2 * world * 8 + 256]
+        self._own, handles = [], []
+        for nb in sizes:
+            ptr = ctypes.c_void_p(0)
+            hbuf = ctypes.create_string_buffer(64)
+            check(lib.pdmrg_ipc_alloc(nb, ctypes.byref(ptr), hbuf), "pdmrg_ipc_alloc")
+            self._own.append(ptr)
+            handles.append(hbuf.raw)
+        mask = ctypes.c_uint(0)
+        check(lib.pdmrg_heff_needed_j(self.plan._plan, 0, ctypes.byref(mask)), "pdmrg_heff_needed_j")
+        mine = (handles, int(mask.value))
+        if world > 1:
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+        else:
+            everyone = [mine]
+        self._opened = []
+        tables = []
+        for k in range(3):
+            arr = (ctypes.c_void_p * world)()
+            for q in range(world):
+                if q == rank:
+                    arr[q] = self._own[k].value
+                else:
+                    ptr = ctypes.c_void_p(0)
+                    check(lib.pdmrg_ipc_open(everyone[q][0][k], ctypes.byref(ptr)), "pdmrg_ipc_open")
+                    self._opened.append(ptr)
+                    arr[q] = ptr.value
+            tables.append(arr)
+        self._jmask = (ctypes.c_uint * world)(*[everyone[q][1] for q in range(world)])
+        self._comm = ctypes.c_void_p(0)
+        check(lib.pdmrg_comm_create(ctypes.byref(self._comm), rank, world, tables[0], tables[1], tables[2]), "pdmrg_comm_create")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def apply(self, x, y, sign=-1.0):
+        from . import device as D
+        pl = self.plan
+        ws = pl.workspace.get(pl.ws_bytes)
+        self._check(self._lib.pdmrg_heff_apply_fused(pl._plan, self._comm, pl._Lp, pl._Rp, D._ptr(x), D._ptr(y), float(sign),
+                                                     self._jmask, D._ptr(ws), ws.numel(), D._stream()), "pdmrg_heff_apply_fused")
+        return y
+
+    def close(self):
+        import torch
+        if getattr(self, "_comm", None):
+            torch.cuda.synchronize()
+            self._lib.pdmrg_comm_destroy(self._comm)
+            self._comm = None
+            for p in self._opened:
+                self._lib.pdmrg_ipc_close(p)
+            for p in self._own:
+                self._lib.pdmrg_ipc_free(p)
+            self._opened, self._own = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
