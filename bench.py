@@ -313,9 +313,24 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         per, ideal = parallel.partition_cost(sh.partition[0])
-        line["sharded"] = {"what": "one chi=%d two-site mat-vec split over the MPO bond, 1 NCCL all-reduce of y (64 MiB)" % chi,
-                           "ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
+        line["sharded"] = {"what": "one chi=%d two-site mat-vec (dense ASEP W) split over the MPO bond" % chi,
+                           "nccl_allreduce": {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9},
                            "scaling": "strong", "slab_gemms_per_rank": per, "ideal_speedup": ideal}
+        # same decomposition, exchange fused into the kernels over peer memory (no NCCL on the data path)
+        fz = parallel.FusedShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist)
+        for _ in range(3):
+            fz.apply(xs, ys)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            fz.apply(xs, ys)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["sharded"]["fused_peer_memory"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
+                                                "how": "GEMM scatter epilogue (peer st.global) + flag-guarded reduce/all-gather kernel"}
+        fz.close()
 
     # ---- extras on rank 0 at N=1: bond step, sweep estimate, CPU baseline ----------------------
     if world == 1 and not args.no_extras:
