@@ -180,6 +180,28 @@ int pdmrg_vec_normalize(int dtype, long long n, const void* in, const double* no
                         void* out, void* stream);
 size_t pdmrg_vec_scratch_bytes(int m);
 
+/* ---- the whole local eigensolve behind one call (K + D: tools/la_tools.py:402-557 as driven by
+ * tools/diag_tools.py:243-290) -------------------------------------------------------------------
+ * Restarted non-symmetric Davidson on the operator  sign * H_eff  of `plan` (the reference minimises
+ * Re of -H, i.e. sign = -1): same subspace growth, restart rule (space + nroots > 12 + 3*nroots),
+ * lindep pruning and stopping rule as the reference; res_tol < 0 keeps the reference's effective
+ * criterion ||r||^2 <= lindep.  x0: nx0 <= nroots guesses (device, x0_stride apart).  XS / AX:
+ * basis and image slabs with >= max_space + 4*nroots rows of `stride` elements; Rv: 2*nroots + 2
+ * rows.  e_out_host: nroots (re, im) pairs; vecs_out: nroots Ritz vectors.  SYNCHRONISES the stream
+ * twice per cycle (O(m) scalars).  The projected eigenproblem is solved on the host by a complex
+ * Hessenberg-QR (pdmrg_host_eig exposes it for testing). */
+size_t pdmrg_davidson_scratch_bytes(int nroots, int max_space);
+int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs, double sign,
+                   int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
+                   double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                   void* XS, void* AX, void* Rv, long long stride,
+                   void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
+                   double* e_out_host, void* vecs_out, long long vecs_stride,
+                   int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream);
+/* eigenvalues w (n complex) and unit-norm right eigenvectors (columns of v) of a small general
+ * complex matrix, column-major interleaved; host only (no GPU needed) */
+int pdmrg_host_eig(int n, const double* a_colmajor_interleaved, double* w_out, double* v_out);
+
 /* ---- truncation ---------------------------------------------------------------------------
  * T2 (tools/mps_tools.py:98-120): thin SVD of a row-major (rows x cols) matrix a:
  *   a = U diag(S) Vh,  U (rows x k) row-major, S (k) descending, Vh (k x cols) row-major,

@@ -67,6 +67,10 @@ def _load():
         "pdmrg_vec_project": (i, [i, ll, i, vp, ll, vp, vp, vp, vp, vp, sz, vp]),
         "pdmrg_vec_normalize": (i, [i, ll, vp, vp, vp, vp]),
         "pdmrg_vec_scratch_bytes": (sz, [i]),
+        "pdmrg_davidson_scratch_bytes": (sz, [i, i]),
+        "pdmrg_davidson": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz, vp, sz,
+                               POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp]),
+        "pdmrg_host_eig": (i, [i, POINTER(d), POINTER(d), POINTER(d)]),
         "pdmrg_svd_workspace_bytes": (sz, [i, i, i, i]),
         "pdmrg_svd": (i, [i, i, i, vp, vp, vp, vp, i, vp, sz, vp, vp]),
         "pdmrg_svd_topk": (i, [i, i, i, i, vp, vp, vp, vp, i, vp, sz, vp, vp]),

@@ -18,11 +18,15 @@ The in-loop orthogonalisation is block classical Gram-Schmidt (one multi-dot pas
 multi-axpy pass) instead of the reference's sequential modified Gram-Schmidt (:524-527);
 both project the same residual against the same orthonormal basis and agree to rounding.
 """
+import ctypes
+import os
+
 import numpy as np
 import scipy.linalg as sla
 import torch
 
 from . import device as D
+from ._lib import check, lib
 
 
 def pick_lowest_real(w, v):
@@ -42,6 +46,8 @@ class DavidsonWorkspace:
         self.R = torch.empty((2 * nroots + 2, n), dtype=dt, device=device)   # residual / Ritz vectors
         self.small = torch.zeros(2 * rows * (nroots + 2) + 16, dtype=dt, device=device)
         self.norms = torch.zeros(2 * nroots + 16, dtype=torch.float64, device=device)
+        self.native_scratch = torch.zeros(int(lib.pdmrg_davidson_scratch_bytes(nroots, 12)) + 256, dtype=torch.uint8,
+                                          device=device)
         self._ops = {}
 
     def ops(self, n):
@@ -88,18 +94,53 @@ def _orthonormalise(ops, src, dst, norm_slot, small):
     return out
 
 
+def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
+                    res_tol=None, fixed_cycles=None, stats=None, sign=-1.0):
+    """The same solver sequenced in C++ (csrc/davidson.cu, ``pdmrg_davidson``): one C-ABI call per
+    local eigenproblem, operator = ``sign`` * H_eff of ``plan``."""
+    ms = max_space + 3 * nroots
+    rows = ms + nroots
+    W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
+    for k, g in enumerate(x0):
+        W.R[nroots + k][:n].copy_(g)
+    out = torch.empty((nroots, n), dtype=W.XS.dtype, device=device)
+    e_host = (ctypes.c_double * (2 * nroots))()
+    n_mv, cyc, last = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+    ws = plan.workspace.get(plan.ws_bytes)
+    check(lib.pdmrg_davidson(plan._plan, plan._Lp, plan._Rp, float(sign), code, n, D._ptr(W.R[nroots]), W.R.stride(0),
+                             len(x0), nroots, max_space, float(lindep), -1.0 if res_tol is None else float(res_tol),
+                             int(max_cycle), int(fixed_cycles or 0), D._ptr(W.XS), D._ptr(W.AX), D._ptr(W.R),
+                             W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
+                             e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last),
+                             D._stream()), "pdmrg_davidson")
+    plan.n_apply += n_mv.value
+    nr = min(nroots, max(1, min(nroots, n)))
+    e = np.array([complex(e_host[2 * k], e_host[2 * k + 1]) for k in range(nr)])
+    if stats is not None:
+        stats["n_matvec"] = stats.get("n_matvec", 0) + n_mv.value
+        stats["cycles"] = stats.get("cycles", 0) + cyc.value
+        stats["last_residual"] = last.value
+    return e, [out[k] for k in range(nr)]
+
+
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
-             res_tol=None, fixed_cycles=None, stats=None):
+             res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
     x0: list of device vectors (initial guesses).  Returns (e ndarray (k,), [k device vectors]).
     ``res_tol``: optional residual-norm stop; default is the reference's effective criterion,
     ||r||^2 <= lindep.  ``fixed_cycles``: stop after exactly that many cycles (benchmarking).
+    When the H_eff ``plan`` is given the loop runs in C++ (``pdmrg_davidson``) unless
+    ``native=False`` / PDMRG_PY_DAVIDSON=1; this Python loop is the specification it mirrors.
     """
     if not isinstance(x0, (list, tuple)):
         x0 = [x0]
     x0 = list(x0)
+    if native is None:
+        native = os.environ.get("PDMRG_PY_DAVIDSON", "0") != "1"
+    if native and plan is not None and nroots <= 4 and len(x0) <= nroots and n > nroots:
+        return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats)
     max_space = max_space + 3 * nroots
     rows = max_space + nroots
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)

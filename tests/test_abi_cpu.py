@@ -97,3 +97,22 @@ def test_combined_operator_matches_oracle_dense():
     Wc1 = combine_onesite(W1, w, w, d, np.float64).reshape(w, d, w, d)
     H1 = np.einsum("pnm,nojl,ijk->opilmk", L, Wc1, R).reshape(d * Dl * Dr, -1)
     assert np.allclose(H1, orc.heff_dense_onesite([L], [W1], [R], (d, Dl, Dr)))
+
+
+def test_host_eig_matches_numpy(lib):
+    """The small general eigen-solver inside pdmrg_davidson (host side; no GPU needed)."""
+    import ctypes
+    rng = np.random.default_rng(0)
+    dp = ctypes.POINTER(ctypes.c_double)
+    for n in (1, 2, 3, 7, 15, 18, 33):
+        for real in (False, True):
+            a = rng.standard_normal((n, n)) + (0 if real else 1j) * rng.standard_normal((n, n))
+            a = a.astype(np.complex128)
+            buf = np.ascontiguousarray(a.T).view(np.float64).ravel()          # column-major, interleaved
+            w = np.zeros(2 * n); v = np.zeros(2 * n * n)
+            assert lib.lib.pdmrg_host_eig(n, buf.ctypes.data_as(dp), w.ctypes.data_as(dp), v.ctypes.data_as(dp)) == 0
+            wc = w.view(np.complex128); vc = v.view(np.complex128).reshape(n, n).T
+            assert np.abs(a @ vc - vc * wc).max() < 1e-11 * max(1.0, np.abs(a).max())
+            ref = np.linalg.eigvals(a)
+            assert max(min(abs(x - ref)) for x in wc) < 1e-9 * max(1.0, abs(ref).max())
+            assert np.allclose(np.linalg.norm(vc, axis=0), 1.0)

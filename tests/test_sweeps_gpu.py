@@ -46,8 +46,16 @@ def test_davidson_golden(P, ctx, golden):
     plan, shape = P.eigs.make_plan(M, [[None, W, None]], F, 1, True, ctx)
     stats = {}
     e, vecs = P.davidson.davidson(lambda x, y: plan.apply(x, y, -1.0), [ctx.dev(x0.ravel())], plan.n, ctx.code,
-                                  ctx.device, nroots=1, stats=stats)
+                                  ctx.device, nroots=1, stats=stats)               # Python loop (no plan given)
     assert abs(e[0] - g["eval"]) < 1e-9 * abs(g["eval"])
+    # the C++ loop (pdmrg_davidson) runs the same algorithm: same eigenvalue, same mat-vec count +- a cycle or two
+    st2 = {}
+    e_n, vecs_n = P.davidson.davidson(None, [ctx.dev(x0.ravel())], plan.n, ctx.code, ctx.device, nroots=1, stats=st2,
+                                      plan=plan, native=True)
+    assert abs(e_n[0] - e[0]) < 1e-10 * abs(e[0])
+    assert abs(st2["n_matvec"] - stats["n_matvec"]) <= max(4, int(0.1 * stats["n_matvec"]))
+    vn = vecs_n[0].cpu().numpy()
+    assert abs(abs(np.vdot(vn, g["evec"])) / (np.linalg.norm(vn) * np.linalg.norm(g["evec"])) - 1) < 1e-10
     v, vr = vecs[0].cpu().numpy(), g["evec"]
     assert abs(abs(np.vdot(v, vr)) / (np.linalg.norm(v) * np.linalg.norm(vr)) - 1) < 1e-10
     assert abs(stats["n_matvec"] - int(g["n_matvec"])) <= max(4, int(0.1 * int(g["n_matvec"])))
