@@ -17,8 +17,6 @@ Layouts (kept identical to the reference):
   mpo[site]  : (wl, wr, d_out, d_in) or None   mpo/asep.py:61-66, tools/diag_tools.py:113-119
   env[k]     : (D_bra, w, D_ket), k = 0..N     tools/env_tools.py:6-26
 """
-import copy
-
 import numpy as np
 import scipy.linalg as sla
 

@@ -36,9 +36,6 @@ struct pdmrg_heff_plan {
 
 namespace {
 
-template <typename T>
-bool is_zero(const T* p) { return p[0] == 0.0; }
-
 int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mpo, const int* wL,
                const int* wR, const void* const* Wc_host, const unsigned char* const* mask) {
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "heff plan: bad dtype");

@@ -137,11 +137,10 @@ def renorm_inf(mpsList, mpoList, envList, vecs, mbd, ctx=None):
 # one-site reduced-density-matrix route
 # ---------------------------------------------------------------------------------------
 def _spectrum_from_rdm(w, keep):
-    """Schmidt spectrum of the cut from RDM eigenvalues (ascending from heevd)."""
+    """Schmidt spectrum of the cut from RDM eigenvalues (ascending from heevd): the reference takes
+    the singular values of the whole (d*Dl, Dr) matrix (dmrg.py:30-37), i.e. sqrt of every eigenvalue."""
     lam = np.clip(w[::-1], 0.0, None)                           # descending, >= 0
-    S = np.sqrt(lam)
-    nz = S[: max(keep, 1)]
-    return calc_entanglement(S if S.size else nz)
+    return calc_entanglement(np.sqrt(lam))
 
 
 def rdm_renormalize_right(psis, shape, nxts, ctx, n_avg=None):
