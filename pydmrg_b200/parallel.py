@@ -43,33 +43,104 @@ def block_pattern(Wc, wL, wR, P):
 
 
 def partition_blocks(pattern, world):
-    """Greedy balanced partition of the non-zero (j, o) blocks over ``world`` ranks.
+    """Balanced partition of the non-zero (j, o) blocks over ``world`` ranks.
 
     The cost of a rank is the number of chi^3 slab GEMMs it must run: |{o}| stage-A slabs plus
-    |{j}| stage-C slabs of the blocks it owns.  Returns a list of ``world`` uint8 masks of
-    shape (wL, wR) that partition ``pattern``."""
+    |{j}| stage-C slabs of the blocks it owns.  Greedy seeding followed by a local search (single
+    block moves and pair swaps that lower the (max, sum of squares) cost).  Returns a list of
+    ``world`` uint8 masks of shape (wL, wR) that partition ``pattern``."""
     wL, wR = pattern.shape
     blocks = [(j, o) for j in range(wL) for o in range(wR) if pattern[j, o]]
-    # visit blocks of the densest row/column first so that they end up grouped
     rowc, colc = pattern.sum(axis=1), pattern.sum(axis=0)
     blocks.sort(key=lambda b: -(rowc[b[0]] + colc[b[1]]))
-    owners = [dict(J=set(), O=set(), blocks=[]) for _ in range(world)]
+    owner = {}
 
-    def cost(ow, extra=None):
-        J, O = set(ow["J"]), set(ow["O"])
-        if extra is not None:
-            J.add(extra[0]); O.add(extra[1])
-        return len(J) + len(O)
+    def cost_of(bl):
+        return len({b[0] for b in bl}) + len({b[1] for b in bl}) if bl else 0
 
-    for b in blocks:
-        # rank whose cost AFTER taking the block is smallest; ties -> smaller increase
-        best = min(range(world), key=lambda r: (cost(owners[r], b), cost(owners[r], b) - cost(owners[r]), r))
-        owners[best]["J"].add(b[0]); owners[best]["O"].add(b[1]); owners[best]["blocks"].append(b)
+    def groups():
+        g = [[] for _ in range(world)]
+        for b, r in owner.items():
+            g[r].append(b)
+        return g
+
+    def score(g):
+        c = [cost_of(x) for x in g]
+        return (max(c), sum(v * v for v in c))
+
+    for b in blocks:                                   # greedy seed
+        g = groups()
+        best = min(range(world), key=lambda r: (cost_of(g[r] + [b]), cost_of(g[r] + [b]) - cost_of(g[r]), r))
+        owner[b] = best
+    improved = True
+    while improved:                                    # local search
+        improved = False
+        cur = score(groups())
+        for b in blocks:
+            r0 = owner[b]
+            for r in range(world):
+                if r == r0:
+                    continue
+                owner[b] = r
+                sc = score(groups())
+                if sc < cur:
+                    cur, improved, r0 = sc, True, r
+                else:
+                    owner[b] = r0
+        for a in blocks:
+            for b in blocks:
+                if owner[a] == owner[b]:
+                    continue
+                owner[a], owner[b] = owner[b], owner[a]
+                sc = score(groups())
+                if sc < cur:
+                    cur, improved = sc, True
+                else:
+                    owner[a], owner[b] = owner[b], owner[a]
+    # small patterns (the MPOs of the reference have <= ~20 blocks): exact branch and bound on the
+    # maximum cost, seeded with the local-search result, ranks filled in canonical order
+    best = {"score": score(groups()), "owner": dict(owner)}
+    budget = [200000]
+    rows = [set() for _ in range(world)]
+    cols = [set() for _ in range(world)]
+    assign = {}
+
+    def rec(i, used):
+        if budget[0] <= 0:
+            return
+        budget[0] -= 1
+        cur_max = max((len(rows[r]) + len(cols[r])) for r in range(world))
+        if cur_max > best["score"][0]:
+            return
+        if i == len(blocks):
+            sc = (cur_max, sum((len(rows[r]) + len(cols[r])) ** 2 for r in range(world)))
+            if sc < best["score"]:
+                best["score"], best["owner"] = sc, dict(assign)
+            return
+        j, o = blocks[i]
+        for r in range(min(used + 1, world)):
+            addj, addo = j not in rows[r], o not in cols[r]
+            if addj:
+                rows[r].add(j)
+            if addo:
+                cols[r].add(o)
+            assign[(j, o)] = r
+            rec(i + 1, max(used, r + 1))
+            if addj:
+                rows[r].discard(j)
+            if addo:
+                cols[r].discard(o)
+        assign.pop((j, o), None)
+
+    if len(blocks) <= 24:
+        rec(0, 0)
+    owner = best["owner"]
     masks = []
-    for ow in owners:
+    for r in range(world):
         m = np.zeros((wL, wR), dtype=np.uint8)
-        for j, o in ow["blocks"]:
-            m[j, o] = 1
+        for (j, o), rr in owner.items():
+            if rr == r:
+                m[j, o] = 1
         masks.append(m)
     return masks
 
