@@ -331,6 +331,20 @@ def main():
         line["sharded"]["fused_peer_memory"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
                                                 "how": "GEMM scatter epilogue (peer st.global) + flag-guarded reduce/all-gather kernel"}
         fz.close()
+        # ket-index sharding: every rank does 1/N of both GEMM stages, one NCCL all-reduce
+        kz = parallel.ShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist, mode="ket")
+        for _ in range(3):
+            kz.apply(xs, ys)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            kz.apply(xs, ys)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["sharded"]["ket_split_nccl"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
+                                             "how": "left ket index split N ways (balanced), 1 NCCL all-reduce of y"}
 
     # ---- extras on rank 0 at N=1: bond step, sweep estimate, CPU baseline ----------------------
     if world == 1 and not args.no_extras:

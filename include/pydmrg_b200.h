@@ -138,6 +138,13 @@ int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, cons
                           long long ldc, long long strideC1, long long strideC2,
                           double alpha_re, double alpha_im, void* stream);
 
+/* Ket-split shard: this rank contracts only the ket indices k in [k0, k0+klen) of the LEFT bond
+ * (x[pin, k, s], L[i, j, k]); x and y keep their full (P, Dl, Dr) shape, y holds the PARTIAL sum.
+ * Perfectly balanced for any rank count (every rank does 1/n of both GEMM stages); combine with a
+ * block mask (or pass NULL) as needed.  klen = 0 makes the rank a no-op (y = 0). */
+int pdmrg_heff_plan_create_ketsplit(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                    const int* wL_host, const int* wR_host, const void* const* Wc_host,
+                                    const unsigned char* const* block_mask_host, int k0, int klen);
 /* algorithmic FLOPs of one apply (dense-W count of SURVEY 8d) and with block sparsity */
 double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan);
 double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan);

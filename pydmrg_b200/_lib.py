@@ -40,6 +40,7 @@ def _load():
         "pdmrg_permute4": (i, [i, vp, vp, i, i, i, i, ll, ll, ll, ll, i, vp, i, vp]),
         "pdmrg_heff_plan_create": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp)]),
         "pdmrg_heff_plan_create_sharded": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp)]),
+        "pdmrg_heff_plan_create_ketsplit": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), i, i]),
         "pdmrg_heff_plan_destroy": (None, [vp]),
         "pdmrg_heff_workspace_bytes": (sz, [vp]),
         "pdmrg_heff_apply": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp]),

@@ -67,6 +67,7 @@ reduce_gather_kernel(const double* __restrict__ Zloc, PeerPtrs Y, const unsigned
     const long long dst = po * Dl * rowlen + (long long)rank * chunk * rowlen + e;
     for (int q = 0; q < world; ++q) Y.p[q][dst] = acc;          // all-gather by peer stores
   }
+  __threadfence_system();      // the pushes are released to the peers by the flag kernel that follows
 }
 
 __global__ void __launch_bounds__(256)

@@ -205,6 +205,11 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
       }
+      // The stage may only be handed back once every lane's LDS of it has been PERFORMED, not merely
+      // issued: ptxas turns the converged __syncwarp into a NOP and schedules the arrive right behind the
+      // last LDS, and under load/store-unit back-pressure (peer stores of sibling warps in the scatter
+      // epilogue) the arrive was observed to overtake them -- TMA then refilled rows still being read.
+      __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -269,6 +274,9 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    // peer stores of this tile must be visible system-wide before the kernel retires: the flag that
+    // releases them to the owner rank is written by a later, stream-ordered kernel
+    if (SCATTER) __threadfence_system();
   }
 }
 

@@ -32,16 +32,21 @@ struct pdmrg_heff_plan {
   void* dev_blob = nullptr;
   double flops_dense = 0, flops_sparse = 0, flops_gemm = 0;
   size_t ws_bytes = 0;
+  int k0 = 0, kl = 0;      // ket-index range [k0, k0+kl) of the LEFT bond this plan contracts (kl = Dl: all)
 };
 
 namespace {
 
 int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mpo, const int* wL,
-               const int* wR, const void* const* Wc_host, const unsigned char* const* mask) {
+               const int* wR, const void* const* Wc_host, const unsigned char* const* mask, int k0 = 0, int klen = -1) {
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "heff plan: bad dtype");
   PDMRG_REQUIRE(P > 0 && Dl > 0 && Dr > 0 && n_mpo > 0, "heff plan: bad extents");
+  if (klen < 0) klen = Dl;
+  PDMRG_REQUIRE(k0 >= 0 && klen >= 0 && k0 + klen <= Dl, "heff plan: ket range outside the left bond");
   auto* pl = new pdmrg_heff_plan();
   pl->dtype = dtype; pl->P = P; pl->Dl = Dl; pl->Dr = Dr; pl->n_mpo = n_mpo;
+  pl->k0 = k0; pl->kl = klen;
+  const int kl = klen;
   const int E = dtype == PDMRG_C128 ? 2 : 1;
   const double cmac = dtype == PDMRG_C128 ? 8.0 : 2.0;
   std::vector<MixOpHost> hosts(n_mpo);
@@ -65,7 +70,7 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
             const double* w = W + (size_t)E * ((size_t)row * cols + o * P + pi);
             const bool nz = (w[0] != 0.0) || (E == 2 && w[1] != 0.0);
             if (!nz) continue;
-            h.in_off.push_back(((long long)o * P + pi) * Dl);
+            h.in_off.push_back(((long long)o * P + pi) * kl);
             h.val.push_back(w[0]);
             h.val.push_back(E == 2 ? w[1] : 0.0);
             need_o[o] = 1; need_j[j] = 1;
@@ -73,7 +78,7 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
           }
         }
         h.rowptr.push_back((int)h.in_off.size());
-        h.out_off.push_back((long long)po * Dr * wl * Dl + (long long)j * Dl);
+        h.out_off.push_back((long long)po * Dr * wl * kl + (long long)j * kl);
       }
     // drop rows of slabs j that are never read by stage C
     MixOpHost hc;
@@ -96,11 +101,11 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
     int no = 0, nj = 0;
     for (int v : need_o) no += v;
     for (int v : need_j) nj += v;
-    const double cube_a = (double)Dr * Dr * Dl, cube_c = (double)Dl * Dl * Dr;
-    pl->flops_dense += cmac * (P * (wr * cube_a + wl * cube_c) + (double)rows * cols * Dl * Dr);
-    pl->flops_sparse += cmac * (P * (no * cube_a + nj * cube_c) + (double)nnz * Dl * Dr);
+    const double cube_a = (double)Dr * Dr * kl, cube_c = (double)Dl * kl * Dr;
+    pl->flops_dense += cmac * (P * (wr * cube_a + wl * cube_c) + (double)rows * cols * kl * Dr);
+    pl->flops_sparse += cmac * (P * (no * cube_a + nj * cube_c) + (double)nnz * kl * Dr);
     pl->flops_gemm += cmac * P * (no * cube_a + nj * cube_c);
-    const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl, u_elems = (size_t)P * Dr * wl * Dl;   // T also hosts Z
+    const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl, u_elems = (size_t)P * Dr * wl * kl;   // T also hosts Z
     const size_t need = align_up(t_elems * 8 * E, 256) + align_up(u_elems * 8 * E, 256);
     if (need > pl->ws_bytes) pl->ws_bytes = need;
   }
@@ -130,6 +135,12 @@ extern "C" int pdmrg_heff_plan_create_sharded(pdmrg_heff_plan** plan, int dtype,
                                               const int* wL, const int* wR, const void* const* Wc_host,
                                               const unsigned char* const* block_mask_host) {
   return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, block_mask_host);
+}
+
+extern "C" int pdmrg_heff_plan_create_ketsplit(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                               const int* wL, const int* wR, const void* const* Wc_host,
+                                               const unsigned char* const* block_mask_host, int k0, int klen) {
+  return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, block_mask_host, k0, klen);
 }
 
 extern "C" void pdmrg_heff_plan_destroy(pdmrg_heff_plan* plan) {
@@ -209,23 +220,35 @@ int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* cons
     for (int j = 0; j < wl; ++j) if (pl->need_j[m][j]) jlist.push_back(j);
     if (olist.empty() || jlist.empty()) continue;
     PDMRG_REQUIRE(olist.size() <= 32 && jlist.size() <= 32, "pdmrg_heff_apply: MPO bond dimension above 32 not supported yet");
-    if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, P * Dl, Dr, 1, (int)olist.size(), olist.data(),
-                               R, (long long)wr * Dr, 0, Dr,
-                               x, Dr, 0, 0, 0,
-                               T, (long long)wr * P * Dl, 0, (long long)P * Dl,
-                               1.0, 0.0, 0, stream))
-      return 1;
+    const int kl = pl->kl, k0 = pl->k0;
+    if (kl == 0) continue;
+    if (kl == Dl) {
+      if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, P * Dl, Dr, 1, (int)olist.size(), olist.data(),
+                                 R, (long long)wr * Dr, 0, Dr,
+                                 x, Dr, 0, 0, 0,
+                                 T, (long long)wr * P * Dl, 0, (long long)P * Dl,
+                                 1.0, 0.0, 0, stream))
+        return 1;
+    } else {
+      // ket-split shard: only the rows k in [k0, k0+kl) of every x[pin] block enter (batch level 1 = pin)
+      if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, kl, Dr, P, (int)olist.size(), olist.data(),
+                                 R, (long long)wr * Dr, 0, Dr,
+                                 static_cast<const double*>(x) + (size_t)E * k0 * Dr, Dr, (long long)Dl * Dr, 0, 0,
+                                 T, (long long)wr * P * kl, kl, (long long)P * kl,
+                                 1.0, 0.0, 0, stream))
+        return 1;
+    }
     // ---- mix
     if (tm && tm->mark(1)) return 1;
-    if (launch_mix(pl->dtype, pl->mix[m], T, U, Dr, Dl, (long long)wr * P * Dl, 1, (long long)wl * Dl, 1, stream)) return 1;
+    if (launch_mix(pl->dtype, pl->mix[m], T, U, Dr, kl, (long long)wr * P * kl, 1, (long long)wl * kl, 1, stream)) return 1;
     if (tm && tm->mark(2)) return 1;
     // ---- stage C: split over the MPO bond j (ONE launch, P x |j| batches, K = Dl each) into the slabs
     //      Z[pout][j][i][r] (aliases T, which is dead after the mix), then an ordered reduction over j:
     //      removes the partial-wave tail of the long-K formulation and fills the GPU at small chi.
     double* Z = T;
-    if (pdmrg_gemm_nt_batched2(pl->dtype, Dl, Dr, Dl, P, (int)jlist.size(), jlist.data(),
-                               L, (long long)wl * Dl, 0, Dl,
-                               U, (long long)wl * Dl, (long long)Dr * wl * Dl, Dl, 0,
+    if (pdmrg_gemm_nt_batched2(pl->dtype, Dl, Dr, kl, P, (int)jlist.size(), jlist.data(),
+                               L + (size_t)E * k0, (long long)wl * Dl, 0, Dl,
+                               U, (long long)wl * kl, (long long)Dr * wl * kl, kl, 0,
                                Z, Dr, (long long)wl * Dl * Dr, (long long)Dl * Dr,
                                1.0, 0.0, 0, stream))
       return 1;
@@ -271,6 +294,7 @@ extern "C" int pdmrg_heff_apply_fused(pdmrg_heff_plan* pl, pdmrg_comm* comm, con
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(pl && comm, "pdmrg_heff_apply_fused: null plan / communicator");
   PDMRG_REQUIRE(pl->n_mpo == 1, "pdmrg_heff_apply_fused: one MPO term per plan");
+  PDMRG_REQUIRE(pl->kl == pl->Dl, "pdmrg_heff_apply_fused: ket-split plans use the all-reduce path");
   PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply_fused: workspace too small");
   const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
   const int P = pl->P, Dl = pl->Dl, Dr = pl->Dr, wl = pl->wL[0], wr = pl->wR[0];

@@ -127,7 +127,7 @@ class HeffPlan:
     ``ops`` is a list over MPO terms of (L, Wc, R): L (Dl,wL,Dl), R (Dr,wR,Dr) CUDA tensors
     and Wc the combined local operator (host ndarray, (wL*P, wR*P))."""
 
-    def __init__(self, code, P, Dl, Dr, ops, workspace, block_masks=None):
+    def __init__(self, code, P, Dl, Dr, ops, workspace, block_masks=None, k_range=None):
         self.code, self.P, self.Dl, self.Dr = code, P, Dl, Dr
         self.n = P * Dl * Dr
         self.Ls = [o[0] for o in ops]
@@ -147,7 +147,14 @@ class HeffPlan:
                 raise ValueError("combined operator shape %s != %s" % (self._wc[k].shape, (wL[k] * P, wR[k] * P)))
         wc_ptrs = (ctypes.c_void_p * n_mpo)(*[w.ctypes.data for w in self._wc])
         self._plan = ctypes.c_void_p(0)
-        if block_masks is None:
+        if k_range is not None:
+            mptrs = None
+            if block_masks is not None:
+                self._masks = [np.ascontiguousarray(m, dtype=np.uint8) for m in block_masks]
+                mptrs = (ctypes.c_void_p * n_mpo)(*[m.ctypes.data for m in self._masks])
+            check(lib.pdmrg_heff_plan_create_ketsplit(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR, wc_ptrs,
+                                                      mptrs, int(k_range[0]), int(k_range[1])), "pdmrg_heff_plan_create_ketsplit")
+        elif block_masks is None:
             check(lib.pdmrg_heff_plan_create(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR, wc_ptrs),
                   "pdmrg_heff_plan_create")
         else:

@@ -155,22 +155,48 @@ def partition_cost(masks):
     return per, full / max(max(per), 1)
 
 
-class ShardedHeff:
-    """MPO-bond-sharded mat-vec: y = allreduce_sum( H_r x ), H_r = this rank's blocks."""
+def ket_chunks(Dl, parts, align=16):
+    """Split [0, Dl) into ``parts`` contiguous ranges whose boundaries are multiples of ``align``
+    (keeps every operand of the shard TMA-aligned); trailing ranks may get an empty range."""
+    per = -(-Dl // parts)
+    per = -(-per // align) * align
+    out = []
+    for r in range(parts):
+        lo = min(Dl, r * per)
+        hi = min(Dl, lo + per)
+        out.append((lo, hi - lo))
+    return out
 
-    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist):
+
+class ShardedHeff:
+    """Sharded mat-vec with one all-reduce: y = allreduce_sum( H_r x ).
+
+    mode='bond' : H_r = this rank's (j, o) blocks of the MPO bond (the environment slabs a rank touches
+                  shrink with the rank count -- the memory-sizing mode of SURVEY 8e; the speed-up is
+                  limited by the block structure, e.g. 4x for the ASEP star pattern);
+    mode='ket'  : H_r = all blocks restricted to a contiguous range of the left ket index (every rank does
+                  1/n of both GEMM stages: balanced for any rank count, environments replicated);
+    mode='auto' : 'ket'."""
+
+    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist, mode="bond"):
         from . import device as D
         self.dist, self.world = dist, world
-        masks = []
+        self.mode = "ket" if mode == "auto" else mode
         self.partition = []
-        for (L, Wc, R) in ops:
-            pat = block_pattern(Wc, L.shape[1], R.shape[1], P)
-            parts = partition_blocks(pat, world)
-            self.partition.append(parts)
-            masks.append(parts[rank])
-        self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, block_masks=masks)
+        if self.mode == "bond":
+            masks = []
+            for (L, Wc, R) in ops:
+                pat = block_pattern(Wc, L.shape[1], R.shape[1], P)
+                parts = partition_blocks(pat, world)
+                self.partition.append(parts)
+                masks.append(parts[rank])
+            self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, block_masks=masks)
+        elif self.mode == "ket":
+            self.k_range = ket_chunks(Dl, world)[rank]
+            self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, k_range=self.k_range)
+        else:
+            raise ValueError("mode must be 'bond', 'ket' or 'auto'")
         self.n = self.plan.n
-        self.flops_dense = self.plan.flops_dense      # of the FULL operator? no: of this rank's share
         self.local_flops = self.plan.flops_sparse
 
     def apply(self, x, y, sign=-1.0):

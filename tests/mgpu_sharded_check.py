@@ -25,6 +25,8 @@ def main():
     y_ref = torch.empty_like(x); full.apply(x, y_ref)
     nccl = parallel.ShardedHeff(D.C128, 4, chi, chi, [(L, Wc, R)], ctx.ws, rank, world, dist)
     y_n = torch.empty_like(x); nccl.apply(x, y_n)
+    ket = parallel.ShardedHeff(D.C128, 4, chi, chi, [(L, Wc, R)], ctx.ws, rank, world, dist, mode="ket")
+    y_k = torch.empty_like(x); ket.apply(x, y_k)
     fused = parallel.FusedShardedHeff(D.C128, 4, chi, chi, [(L, Wc, R)], ctx.ws, rank, world, dist)
     y_f = torch.empty_like(x)
     for _ in range(4):
@@ -32,6 +34,7 @@ def main():
     torch.cuda.synchronize()
     e_n = ((y_n - y_ref).norm() / y_ref.norm()).item()
     e_f = ((y_f - y_ref).norm() / y_ref.norm()).item()
+    e_k = ((y_k - y_ref).norm() / y_ref.norm()).item()
     # bit-identical across ranks
     chk = torch.view_as_real(y_f).clone()
     ref0 = chk.clone(); dist.broadcast(ref0, 0)
@@ -50,10 +53,20 @@ def main():
     t_full = timeit(lambda: full.apply(x, y_ref))
     t_nccl = timeit(lambda: nccl.apply(x, y_n))
     t_fused = timeit(lambda: fused.apply(x, y_f))
-    ok = e_n < 1e-13 and e_f < 1e-13 and same
+    t_ket = timeit(lambda: ket.apply(x, y_k))
+    # stress: back-to-back applies with no host synchronisation in between (the exchange flags and the
+    # GEMM's shared-memory ring are the only ordering); every batch must reproduce the reference
+    worst = 0.0
+    for _ in range(int(os.environ.get("PDMRG_CHECK_BATCHES", "12"))):
+        for _ in range(4):
+            fused.apply(x, y_f)
+        torch.cuda.synchronize()
+        worst = max(worst, ((y_f - y_ref).norm() / y_ref.norm()).item())
+    ok = e_n < 1e-13 and e_f < 1e-13 and e_k < 1e-13 and same and worst < 1e-13
     if rank == 0:
-        print("chi %d world %d: err nccl %.2e fused %.2e bit-identical %s | ms unsharded %.3f nccl-sharded %.3f fused-sharded %.3f"
-              % (chi, world, e_n, e_f, same, t_full, t_nccl, t_fused), flush=True)
+        print("chi %d world %d: err bond/nccl %.2e bond/fused %.2e ket/nccl %.2e bit-identical %s stress %.2e | ms unsharded %.3f "
+              "bond+nccl %.3f bond+fused %.3f ket+nccl %.3f"
+              % (chi, world, e_n, e_f, e_k, same, worst, t_full, t_nccl, t_fused, t_ket), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     fused.close()
     dist.barrier()

@@ -190,6 +190,15 @@ def test_heff_linearity_full_size(D, ws):
     p0.apply(x, y0); p1.apply(x, y1)
     torch.cuda.synchronize()
     assert ((y0 + y1) - hx).norm().item() / hx.norm().item() < 1e-13
+    # ket-index sharding: three unequal ranges of the left ket index (one of them empty) sum to the full result
+    acc = torch.zeros_like(x)
+    for k_range in ((0, 192), (192, 320), (512, 0)):
+        pk = D.HeffPlan(D.C128, 4, chi, chi, [(L, Wc, R)], ws, k_range=k_range)
+        yk = torch.empty_like(x)
+        pk.apply(x, yk)
+        acc += yk
+    torch.cuda.synchronize()
+    assert (acc - hx).norm().item() / hx.norm().item() < 1e-13
 
 
 # ---------------------------------------------------------------------------------------
