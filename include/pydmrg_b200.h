@@ -234,6 +234,18 @@ int pdmrg_svd_topk(int dtype, int rows, int cols, int keep, void* a, void* U, do
 size_t pdmrg_left_basis_workspace_bytes(int dtype, int n, int c);
 int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X, void* Ut, double* lam,
                      void* workspace, size_t workspace_bytes, int* info_dev, void* stream);
+/* Warm-started replacement for pdmrg_left_basis in a converging sweep (same role as the SVD of
+ * tools/mps_tools.py:106 for a moving centre; see csrc/solver.cu "Recycled ... step"):
+ *   T = Wt X1^H (K x a)  ->  Householder QR keeping the column order  ->  Pt (K x a, orthonormal rows),
+ *   Ct = Pt X2^T (K x c),  then rows [k-b, K) of Pt and Ct are rotated by the exact Rayleigh-Ritz
+ *   vectors of that window (sorted by decreasing weight);  S[i] = ||Ct[i, :]||.
+ * X1 (a x c) and X2 = X1^T (c x a) are row-major and read-only, Wt (K x c) holds the previous basis
+ * (k kept rows, then K-k spare rows, ordered by weight).  Needs K <= min(a, c).  The caller keeps rows
+ * [0, k).  info_dev receives the last cuSOLVER info. */
+size_t pdmrg_recycle_basis_workspace_bytes(int dtype, int a, int c, int K, int k, int b);
+int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, const void* X1, const void* X2,
+                        const void* Wt, void* Pt, void* Ct, double* S, void* workspace,
+                        size_t workspace_bytes, int* info_dev, void* stream);
 /* T1 (dmrg.py:64-76): eigen-decomposition of a Hermitian (n x n) row-major matrix, in place:
  * on exit row i of `a` is the i-th eigenvector (ascending eigenvalues in w). */
 size_t pdmrg_heevd_workspace_bytes(int dtype, int n);

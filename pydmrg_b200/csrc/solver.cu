@@ -537,6 +537,139 @@ extern "C" int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------
+// Recycled (warm-started) dominant-subspace step for the moving-centre two-site truncation.
+//
+// In a converging sweep the cut's singular subspaces barely move between two visits of the same bond, so
+// the O(n^3) eigen-decomposition of the reduced density matrix can be replaced by ONE step of ordered
+// two-sided subspace iteration started from the previous bases (k kept + p spare vectors, ordered by
+// weight):   T = W X1^H  ->  Householder QR (column order kept, so the nested dominant subspaces and the
+// grading of the columns survive)  ->  P,   C = P X2^T   (the projection of the wave-function on P),
+// followed by an exact Rayleigh-Ritz rotation restricted to the WINDOW [k-b, k+p) around the cut, which is
+// the only place where the kept/discarded split is decided.  Everything is GEMMs on the DMMA kernel plus
+// cuSOLVER geqrf/ungqr and a (b+p)-sized heevd.  The caller alternates X1/X2 = (psi, psi^T) moving right
+// and (psi^T, psi) moving left; see truncate.recycled_truncate for the conjugation bookkeeping.
+// ---------------------------------------------------------------------------------------
+namespace pdmrg {
+namespace {
+
+struct RecycleLayout {
+  size_t tau, H, lam, Tw, lwork_bytes;
+  int lwork_elems;
+  size_t total() const { return tau + H + lam + Tw + lwork_bytes; }
+};
+
+int recycle_layout(Solver* s, int dtype, int a, int c, int K, int w, RecycleLayout* l) {
+  const size_t eb = elem_bytes(dtype);
+  if (w < 1) w = 1;                      // no Rayleigh-Ritz window (plain ordered QR): keep the queries valid
+  l->tau = align_up((size_t)K * eb, 256);
+  l->H = align_up((size_t)w * w * eb, 256);
+  l->lam = align_up((size_t)w * 8, 256);
+  l->Tw = align_up((size_t)w * (size_t)(a > c ? a : c) * eb, 256);
+  int lw_e = 0, lw_q = 0, lw_g = 0;
+  cusolverStatus_t st;
+  if (dtype == PDMRG_C128) {
+    st = s->p_cusolverDnZheevd_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_e);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnZgeqrf_bufferSize(s->handle, a, K, nullptr, a, &lw_q);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnZungqr_bufferSize(s->handle, a, K, K, nullptr, a, nullptr, &lw_g);
+  } else {
+    st = s->p_cusolverDnDsyevd_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_e);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnDgeqrf_bufferSize(s->handle, a, K, nullptr, a, &lw_q);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnDorgqr_bufferSize(s->handle, a, K, K, nullptr, a, nullptr, &lw_g);
+  }
+  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolver bufferSize (recycle) failed (%d)", (int)st); return 1; }
+  int lw = lw_e > lw_q ? lw_e : lw_q;
+  if (lw_g > lw) lw = lw_g;
+  l->lwork_elems = lw;
+  l->lwork_bytes = align_up((size_t)lw * eb, 256) + 256;
+  return 0;
+}
+
+// out[r] = || M[r, :] ||_2 for a row-major (rows x len) matrix of E-word elements; one block per row
+template <int E>
+__global__ void __launch_bounds__(256) row_norm_kernel(const double* __restrict__ M, long long len, double* __restrict__ out) {
+  __shared__ double sm[256];
+  const double* row = M + (size_t)blockIdx.x * len * E;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < len * E; i += 256) { const double v = row[i]; s = fma(v, v, s); }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sqrt(sm[0]);
+}
+
+}  // namespace
+}  // namespace pdmrg
+
+extern "C" size_t pdmrg_recycle_basis_workspace_bytes(int dtype, int a, int c, int K, int k, int b) {
+  Solver* s = get_solver();
+  if (!s) return 0;
+  if (K < 1 || k < 1 || k > K || b < 0 || b > k) { set_error("pdmrg_recycle_basis_workspace_bytes: bad extents"); return 0; }
+  RecycleLayout l;
+  if (recycle_layout(s, dtype, a, c, K, K - (k - b), &l)) return 0;
+  return l.total() + 256;
+}
+
+extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, const void* X1, const void* X2, const void* Wt,
+                                   void* Pt, void* Ct, double* S, void* workspace, size_t workspace_bytes, int* info_dev,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Solver* s = get_solver();
+  if (!s) return 1;
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_recycle_basis: bad dtype");
+  PDMRG_REQUIRE(a > 0 && c > 0 && K > 0 && K <= a && K <= c, "pdmrg_recycle_basis: need 0 < K <= min(a, c)");
+  PDMRG_REQUIRE(k > 0 && k <= K && b >= 0 && b <= k, "pdmrg_recycle_basis: need 0 < k <= K and 0 <= b <= k");
+  const int w0 = k - b, w = K - w0;
+  RecycleLayout l;
+  if (recycle_layout(s, dtype, a, c, K, w, &l)) return 1;
+  PDMRG_REQUIRE(workspace_bytes >= l.total(), "pdmrg_recycle_basis: workspace too small");
+  if (s->p_cusolverDnSetStream(s->handle, stream) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnSetStream failed"); return 1; }
+  const bool cplx = dtype == PDMRG_C128;
+  const size_t eb = elem_bytes(dtype);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  void* tau = ws;
+  void* H = ws + l.tau;
+  double* lam = reinterpret_cast<double*>(ws + l.tau + l.H);
+  void* Tw = ws + l.tau + l.H + l.lam;
+  void* work = ws + l.tau + l.H + l.lam + l.Tw;
+
+  // T[i, r] = sum_x W[i, x] conj(X1[r, x])     (K x a), written where P will live
+  if (pdmrg_gemm_nt(dtype, K, a, c, 1, Wt, c, 0, X1, c, 0, 1, Pt, a, 0, 1.0, 0.0, 0, stream_)) return 1;
+  // Householder QR of the column-major (a x K) view: column i of it is row i of T
+  cusolverStatus_t st;
+  if (cplx) st = s->p_cusolverDnZgeqrf(s->handle, a, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+  else st = s->p_cusolverDnDgeqrf(s->handle, a, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
+  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: geqrf failed (%d)", (int)st); return 1; }
+  if (cplx) st = s->p_cusolverDnZungqr(s->handle, a, K, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+  else st = s->p_cusolverDnDorgqr(s->handle, a, K, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
+  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: ungqr failed (%d)", (int)st); return 1; }
+  count_launch(2);
+  // C[i, x] = sum_r P[i, r] X2[x, r]            (K x c)
+  if (pdmrg_gemm_nt(dtype, K, c, a, 1, Pt, a, 0, X2, a, 0, 0, Ct, c, 0, 1.0, 0.0, 0, stream_)) return 1;
+
+  if (w > 1) {
+    // Rayleigh-Ritz on the window rows [w0, K):  H = -(Cw Cw^H); ascending eigenvalues of -H = descending weights.
+    // Row-major H is column-major conj(H), so after heevd memory row q holds conj(v_q) = the coefficients
+    // Vh[q, i] with which window rows are recombined:  row'_q = sum_i Vh[q, i] row_i  (same for C and P).
+    unsigned char* Cw = static_cast<unsigned char*>(Ct) + (size_t)w0 * c * eb;
+    unsigned char* Pw = static_cast<unsigned char*>(Pt) + (size_t)w0 * a * eb;
+    if (pdmrg_gemm_nt(dtype, w, w, c, 1, Cw, c, 0, Cw, c, 0, 1, H, w, 0, -1.0, 0.0, 0, stream_)) return 1;
+    if (heevd_inplace(s, dtype, w, (double*)H, lam, work, l.lwork_elems, info_dev, stream)) return 1;
+    if (pdmrg_permute4(dtype, Cw, Tw, 1, 1, c, w, 0, 0, 1, c, 0, nullptr, 0, stream_)) return 1;       // Tw[x, i] = Cw[i, x]
+    if (pdmrg_gemm_nt(dtype, w, c, w, 1, H, w, 0, Tw, w, 0, 0, Cw, c, 0, 1.0, 0.0, 0, stream_)) return 1;
+    if (pdmrg_permute4(dtype, Pw, Tw, 1, 1, a, w, 0, 0, 1, a, 0, nullptr, 0, stream_)) return 1;
+    if (pdmrg_gemm_nt(dtype, w, a, w, 1, H, w, 0, Tw, w, 0, 0, Pw, a, 0, 1.0, 0.0, 0, stream_)) return 1;
+  }
+  if (cplx) row_norm_kernel<2><<<K, 256, 0, stream>>>((const double*)Ct, c, S);
+  else row_norm_kernel<1><<<K, 256, 0, stream>>>((const double*)Ct, c, S);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
+  return 0;
+}
+
 extern "C" size_t pdmrg_heevd_workspace_bytes(int dtype, int n) {
   Solver* s = get_solver();
   if (!s) return 0;

@@ -122,7 +122,8 @@ def leftStep(mpsL, W, F, site, nStates=1, alg="davidson", preserveState=False, o
     return E, mpsL, F, EE, EEs
 
 
-def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx=None, stats=None, **solver):
+def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx=None, stats=None, recycle=None,
+                exact_trunc=False, **solver):
     """Two-site bond step on (site, site+1): two-site local solve (tools/diag_tools.py:146-162,
     guess :257), SVD truncation to ``mbd`` (tools/mps_tools.py:98-120), block update
     (tools/env_tools.py:40-50 / 28-38).  The singular values go to the new centre site.
@@ -139,7 +140,8 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
                         stats=stats, return_device=True, **solver)
     tick.lap(stats, "t_eig")
     psi = v[:, 0].contiguous()
-    A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction)
+    A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction, recycle=recycle, site=site,
+                                        warm=(mpsL[0][site], mpsL[0][site + 1]), exact=exact_trunc, stats=stats)
     tick.lap(stats, "t_svd")
     mpsL[0][site] = like(A, proto)
     mpsL[0][site + 1] = like(B, proto)
@@ -192,17 +194,24 @@ def leftSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=Fals
     return Ereturn, mpsL, F, EE, EEs
 
 
-def twoSiteSweep(mpsL, W, F, mbd, alg="davidson", ctx=None, stats=None, sites=None, **solver):
+def twoSiteSweep(mpsL, W, F, mbd, alg="davidson", ctx=None, stats=None, sites=None, recycle=None, **solver):
     """One full two-site sweep: bonds 0..N-2 moving right, then N-2..0 moving left.
-    E / EE / S are recorded at the centre bond (N//2-1, N//2)."""
+    E / EE / S are recorded at the centre bond (N//2-1, N//2).
+
+    ``recycle``: a dict kept by the caller across sweeps of the SAME state and bond dimension; when
+    given, bonds whose previous bases are cached are truncated by the warm-started subspace step
+    (truncate.recycled_truncate) instead of a fresh eigen-decomposition.  The centre bond is always
+    decomposed exactly, so the reported entanglement spectrum never depends on the cache."""
     N = len(mpsL[0])
     E = EE = EEs = S = None
     for site in range(0, N - 1):
-        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "right", mbd, alg=alg, ctx=ctx, stats=stats, **solver)
+        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "right", mbd, alg=alg, ctx=ctx, stats=stats, recycle=recycle,
+                                             exact_trunc=(site == N // 2 - 1), **solver)
         if site == N // 2 - 1:
             E, EE, EEs, S = e, ee, ees, s
     for site in range(N - 2, -1, -1):
-        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "left", mbd, alg=alg, ctx=ctx, stats=stats, **solver)
+        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "left", mbd, alg=alg, ctx=ctx, stats=stats, recycle=recycle,
+                                             exact_trunc=(site == N // 2 - 1), **solver)
         if site == N // 2 - 1:
             E, EE, EEs, S = e, ee, ees, s
     return E, mpsL, F, EE, EEs, S
@@ -235,8 +244,10 @@ def printResults(converged, E, EE, EEspec, gap):
 def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, fname=None, nStates=1,
                targetState=0, alg="davidson", preserveState=False, gaugeSiteLoad=0, gaugeSiteSave=0,
                returnState=False, returnEnv=False, returnEntSpec=False, orthonormalize=False,
-               ctx=None, stats=None, twoSite=False, mbd=None, **solver):
-    """dmrg.py:238-307.  ``mpsL`` / ``F`` may be NumPy lists (they are moved to the device)."""
+               ctx=None, stats=None, twoSite=False, mbd=None, recycle=True, **solver):
+    """dmrg.py:238-307.  ``mpsL`` / ``F`` may be NumPy lists (they are moved to the device).
+    ``recycle``: two-site sweeps after the first reuse each bond's previous singular bases
+    (truncate.truncate_twosite); False decomposes every bond from scratch."""
     ctx = ctx or default_context()
     host_in = not is_dev(mpsL[0][0])
     mpsL = [[ctx.dev(t) for t in M] for M in mpsL]
@@ -249,8 +260,9 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
     if twoSite:
         if mbd is None:
             mbd = mps_tools.maxBondDim([[t for t in mpsL[0]]])
+        cache = {} if recycle else None
         while cont:
-            E, mpsL, F, EE, EEs, S = twoSiteSweep(mpsL, W, F, mbd, alg=alg, ctx=ctx, stats=stats, **solver)
+            E, mpsL, F, EE, EEs, S = twoSiteSweep(mpsL, W, F, mbd, alg=alg, ctx=ctx, stats=stats, recycle=cache, **solver)
             cont, conv, E_prev, iterCnt = checkConv(E_prev, E, tol, iterCnt, maxIter, minIter)
         gaugeSiteSave = 0      # after a left sweep the centre is on site 0
     else:

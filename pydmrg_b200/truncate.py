@@ -56,7 +56,15 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     return A, B, Sn, EE, EEs
 
 
-def eig_truncate(psi, shape, mbd, ctx, direction):
+RECYCLE_FRACTION = 8        # spare vectors p = window depth b = k // RECYCLE_FRACTION (at least 2)
+
+
+def spare_count(k, rows, cols):
+    """Number of spare basis vectors carried beyond the kept k for the recycled truncation."""
+    return max(0, min(max(2, k // RECYCLE_FRACTION), min(rows, cols) - k))
+
+
+def eig_truncate(psi, shape, mbd, ctx, direction, spare=0, extras=None):
     """Projective two-site truncation for a MOVING centre (finite sweeps): only the isometry of the
     side being left behind is needed, so ONE Hermitian eigen-decomposition of the reduced density
     matrix replaces the SVD (same construction as the reference's one-site renormalizeR/L,
@@ -77,10 +85,14 @@ def eig_truncate(psi, shape, mbd, ctx, direction):
     D.permute4(m, mT, (cols, rows), (1, cols))
     X = m if direction == "right" else mT                       # left: eigenvectors of mT mT^H are conj(v_a)
     n = X.shape[0]
-    res = D.left_basis(X, ctx.svd_ws, keep=k)
+    res = D.left_basis(X, ctx.svd_ws, keep=k + spare)
     if res is None:                                             # cuSOLVER did not converge: LAPACK-grade route
         return svd_truncate(psi, shape, mbd, Context_with(ctx, D.SVD_GESVD), absorb=direction)
     Ut, lam_dev, info = res
+    if extras is not None and spare > 0:
+        # the next `spare` eigenvectors seed the recycled truncation of this bond's next visit: rows u_a
+        # (left vectors) after a right-moving step, rows conj(v_a) (right vectors) after a left-moving one
+        extras["ext"] = Ut[k:k + spare].clone()
     lam = np.clip(lam_dev.cpu().numpy()[:k], 0.0, None)
     EE, EEs, Sn = calc_entanglement(np.sqrt(lam))
     A = ctx.empty(d1, Dl, k)
@@ -100,6 +112,92 @@ def eig_truncate(psi, shape, mbd, ctx, direction):
     return A, B, Sn, EE, EEs
 
 
+def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext):
+    """Projective truncation warm-started from the bond's previous bases (csrc/solver.cu
+    pdmrg_recycle_basis; same outputs as eig_truncate plus the new spare rows, or None when it cannot be
+    used).  ``warm`` is the site tensor holding the previous basis of the side that is NOT being left
+    behind: moving right the right-canonical B0 (d2,k,Dr), whose rows b_i^H span the old right space
+    (T = psi B0^H, P = conj(left vectors), C = P^H psi = new centre); moving left the centre-form
+    A0 (d1,Dl,k) = U S (T^T = psi^H A0, P = right vectors, C^T = psi P = new centre)."""
+    d1, d2, Dl, Dr = shape
+    rows, cols = Dl * d1, d2 * Dr
+    k = min(int(mbd), rows, cols)
+    p = ext.shape[0]
+    K = k + p
+    m = ctx.empty(rows, cols)
+    D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
+    mT = ctx.empty(cols, rows)
+    D.permute4(m, mT, (cols, rows), (1, cols))
+    right = direction == "right"
+    a, c, X1, X2 = (rows, cols, m, mT) if right else (cols, rows, mT, m)
+    if K > min(a, c) or ext.shape[1] != c:
+        return None
+    Wt = ctx.empty(K, c)
+    if right:
+        D.permute4(warm, Wt, (k, d2, Dr), (Dr, k * Dr, 1))          # Wt[i,(q,s)] = B0[q,i,s]
+    else:
+        D.permute4(warm, Wt, (k, Dl, d1), (1, k, Dl * k))           # Wt[i,(l,n)] = A0[n,l,i]
+    Wt[k:].copy_(ext)
+    b = min(k, max(2, k // RECYCLE_FRACTION))
+    Pt, Ct, S, info = D.recycle_basis(X1, X2, Wt, k, b, ctx.svd_ws)
+    Sh = S.cpu().numpy()                                            # sync
+    if int(info.item()) != 0 or not np.all(np.isfinite(Sh)):
+        return None
+    EE, EEs, Sn = calc_entanglement(Sh[:k])
+    A = ctx.empty(d1, Dl, k)
+    B = ctx.empty(d2, k, Dr)
+    if right:
+        D.permute4(Pt, A, (d1, Dl, k), (1, d1, a), conj=True)       # A[n,l,i] = conj(P[i,(l,n)])
+        D.permute4(Ct, B, (d2, k, Dr), (Dr, c, 1))                  # B[q,i,s] = C[i,(q,s)]
+    else:
+        D.permute4(Pt, B, (d2, k, Dr), (Dr, a, 1), conj=True)       # B[q,i,s] = conj(P[i,(q,s)])
+        D.permute4(Ct, A, (d1, Dl, k), (1, d1, c))                  # A[n,l,i] = C[i,(l,n)]
+    new_ext = ctx.empty(p, a)
+    D.permute4(Pt[k:], new_ext, (p, a), (a, 1), conj=True)
+    return A, B, Sn, EE, EEs, new_ext
+
+
+def full_rank_split(psi, shape, ctx, direction):
+    """Bond step that discards nothing (k = min(rows, cols), the bonds near the chain ends): any
+    orthonormal basis of the full row / column space is optimal, so no spectrum is needed.  If the side
+    left behind already has dimension k its isometry is the identity; otherwise one ordered Householder
+    QR (pdmrg_recycle_basis with the identity as "previous basis" and no window).  The returned S are
+    the row norms of the centre, NOT Schmidt values (entropies are only reported at the centre bond)."""
+    d1, d2, Dl, Dr = shape
+    rows, cols = Dl * d1, d2 * Dr
+    k = min(rows, cols)
+    m = ctx.empty(rows, cols)
+    D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
+    right = direction == "right"
+    A = ctx.empty(d1, Dl, k)
+    B = ctx.empty(d2, k, Dr)
+    eye = lambda n: torch.eye(n, dtype=ctx.tdtype, device=ctx.device)
+    if right and k == rows:
+        D.permute4(eye(rows), A, (d1, Dl, k), (k, d1 * k, 1))           # A[n,l,i] = delta((l,n), i)
+        D.permute4(m, B, (d2, k, Dr), (Dr, cols, 1))                    # B[q,i,s] = m[i,(q,s)]
+        S = torch.linalg.vector_norm(m, dim=1)
+    elif (not right) and k == cols:
+        D.permute4(eye(cols), B, (d2, k, Dr), (Dr, cols, 1))            # B[q,i,s] = delta(i, (q,s))
+        D.permute4(m, A, (d1, Dl, k), (cols, d1 * cols, 1))             # A[n,l,i] = m[(l,n), i]
+        S = torch.linalg.vector_norm(m, dim=0)
+    else:
+        mT = ctx.empty(cols, rows)
+        D.permute4(m, mT, (cols, rows), (1, cols))
+        a, c, X1, X2 = (rows, cols, m, mT) if right else (cols, rows, mT, m)
+        Pt, Ct, S, info = D.recycle_basis(X1, X2, eye(c), k, 0, ctx.svd_ws)
+        if right:
+            D.permute4(Pt, A, (d1, Dl, k), (1, d1, a), conj=True)
+            D.permute4(Ct, B, (d2, k, Dr), (Dr, c, 1))
+        else:
+            D.permute4(Pt, B, (d2, k, Dr), (Dr, a, 1), conj=True)
+            D.permute4(Ct, A, (d1, Dl, k), (1, d1, c))
+    Sh = S.cpu().numpy()
+    if not np.all(np.isfinite(Sh)) or not np.any(Sh > 0):
+        return None
+    EE, EEs, Sn = calc_entanglement(Sh[:k])
+    return A, B, Sn, EE, EEs
+
+
 def Context_with(ctx, svd_method):
     """Shallow view of a context with another SVD back-end (shares workspaces)."""
     import copy
@@ -108,13 +206,53 @@ def Context_with(ctx, svd_method):
     return c
 
 
-def truncate_twosite(psi, shape, mbd, ctx, direction):
+def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, warm=None, exact=False, stats=None):
     """Truncation used by the finite two-site sweep: projective (one heevd) for large cuts, full SVD
-    (cuSOLVER gesvd) for small ones or when an explicit SVD back-end was requested."""
+    (cuSOLVER gesvd) for small ones or when an explicit SVD back-end was requested.
+
+    ``recycle`` (a dict owned by the sweep driver) switches on the warm-started variant: every exact
+    step also stores the next few singular vectors of the bond, and the following visit of the same
+    bond (``site``, opposite direction) starts from them and from ``warm`` = (mps[site], mps[site+1])
+    instead of diagonalising the reduced density matrix again.  ``exact`` forces the eigen-decomposition
+    (used at the bond whose spectrum is reported)."""
     d1, d2, Dl, Dr = shape
-    if ctx.svd_method < 0 and min(Dl * d1, d2 * Dr) >= 128:
+    rows, cols = Dl * d1, d2 * Dr
+    if not (ctx.svd_method < 0 and min(rows, cols) >= 128):
+        return svd_truncate(psi, shape, mbd, ctx, absorb=direction)
+    if recycle is None:
         return eig_truncate(psi, shape, mbd, ctx, direction)
-    return svd_truncate(psi, shape, mbd, ctx, absorb=direction)
+    right = direction == "right"
+    k = min(int(mbd), rows, cols)
+    p = spare_count(k, rows, cols)
+    other = "left" if right else "right"
+    ext = recycle.get((site, direction))
+    if not exact and k == min(rows, cols):
+        r = full_rank_split(psi, shape, ctx, direction)
+        if r is not None:
+            recycle.pop((site, other), None)
+            if stats is not None:
+                stats["n_full_rank"] = stats.get("n_full_rank", 0) + 1
+            return r
+    if not exact and p > 0 and ext is not None and warm is not None:
+        top = warm[1] if right else warm[0]
+        want = (d2, k, Dr) if right else (d1, Dl, k)
+        if is_dev(top) and tuple(top.shape) == want and top.dtype == ctx.tdtype and ext.dtype == ctx.tdtype \
+                and tuple(ext.shape) == (p, cols if right else rows):
+            r = recycled_truncate(psi, shape, mbd, ctx, direction, top.contiguous(), ext)
+            if r is not None:
+                recycle[(site, other)] = r[5]
+                if stats is not None:
+                    stats["n_recycled"] = stats.get("n_recycled", 0) + 1
+                return r[:5]
+    extras = {}
+    out = eig_truncate(psi, shape, mbd, ctx, direction, spare=p, extras=extras)
+    if "ext" in extras:
+        recycle[(site, other)] = extras["ext"]
+    else:
+        recycle.pop((site, other), None)
+    if stats is not None:
+        stats["n_exact_trunc"] = stats.get("n_exact_trunc", 0) + 1
+    return out
 
 
 def renorm_inf(mpsList, mpoList, envList, vecs, mbd, ctx=None):

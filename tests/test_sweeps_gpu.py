@@ -388,3 +388,98 @@ def test_odd_bond_dimension_f64(P):
     assert E.shape == (3,)
     assert abs(E[2] - top) < 1e-9 * abs(top)         # chi = 8 is exact for N = 7
     assert E[0].real <= E[1].real + 1e-12 <= E[2].real + 2e-12   # variational in chi for the symmetric problem
+
+
+# ---------------------------------------------------------------------------------------
+# warm-started ("recycled") truncation
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("direction", ["right", "left"])
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+def test_recycled_truncate_matches_exact(P, direction, dtype):
+    """One warm-started subspace step from slightly perturbed previous bases reproduces the exact
+    projective truncation: same kept Schmidt values (1e-10 of S_0), same projector on the kept subspace,
+    isometric site tensor, new centre = exact projection of psi."""
+    c = P.core.Context(dtype)
+    rng = np.random.default_rng(3)
+    d1 = d2 = 2
+    Dl, Dr, k = 96, 80, 64
+    rows, cols = Dl * d1, d2 * Dr
+    rnd = (lambda *s: crand(rng, *s)) if dtype == "c128" else (lambda *s: rng.standard_normal(s))
+    U, _ = np.linalg.qr(rnd(rows, rows))
+    V, _ = np.linalg.qr(rnd(cols, cols))
+    q = min(rows, cols)
+    s = np.exp(-np.arange(q) * 0.12)
+    m = (U[:, :q] * s) @ V[:, :q].conj().T
+    psi = m.reshape(Dl, d1, d2, Dr).transpose(1, 2, 0, 3).reshape(-1)
+    p = P.truncate.spare_count(k, rows, cols)
+    # previous bases: exact ones rotated by a small random unitary-ish perturbation
+    eps = 1e-6
+    if direction == "right":
+        Wfull = V[:, : k + p].conj().T + eps * rnd(k + p, cols)          # rows ~ conj(right vectors)^T ... = b_i^H
+        warm = np.ascontiguousarray(Wfull[:k].reshape(k, d2, Dr).transpose(1, 0, 2))         # B0 (d2,k,Dr)
+    else:
+        Wfull = (U[:, : k + p] * np.r_[s[:k], np.ones(p)]).T + eps * rnd(k + p, rows)        # rows ~ s_i u_i^T
+        warm = np.ascontiguousarray(Wfull[:k].reshape(k, Dl, d1).transpose(2, 1, 0))         # A0 (d1,Dl,k)
+    ext = c.dev(np.ascontiguousarray(Wfull[k:]))
+    out = P.truncate.recycled_truncate(c.dev(psi), (d1, d2, Dl, Dr), k, c, direction, c.dev(warm), ext)
+    assert out is not None
+    A, B, Sn, EE, EEs, new_ext = out
+    A, B = c.host(A), c.host(B)
+    Sx = s[:k] / np.linalg.norm(s[:k])
+    assert np.max(np.abs(Sn - Sx)) < 1e-8          # one step from a 1e-6 perturbation (error is second order)
+    Am = A.transpose(1, 0, 2).reshape(rows, k)
+    Bm = B.transpose(1, 0, 2).reshape(k, cols)
+    iso = Am if direction == "right" else Bm.conj().T
+    assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12
+    # the product A.B is the projection of psi on the kept subspace
+    proj = iso @ (iso.conj().T @ m) if direction == "right" else (m @ iso) @ iso.conj().T
+    assert np.max(np.abs(Am @ Bm - proj)) < 1e-12
+    # discarded weight within 1e-10 (relative to ||psi||^2) of the optimum
+    w_opt = np.sum(s[k:] ** 2)
+    w_rec = np.linalg.norm(m) ** 2 - np.linalg.norm(Am @ Bm) ** 2
+    assert w_rec >= w_opt - 1e-13 and w_rec - w_opt < 1e-10 * np.sum(s ** 2)
+    assert tuple(new_ext.shape) == (p, rows if direction == "right" else cols)
+
+
+@pytest.mark.parametrize("model", ["heisenberg_f64", "asep_c128"])
+def test_recycled_sweeps_match_exact_sweeps(P, model):
+    """Two-site sweeps with the warm-started truncation converge to the same fixed point as sweeps that
+    diagonalise every bond from scratch: E to 1e-10 relative, EE to 1e-8 (north-star tolerances), with
+    chi truncating (discarded weight ~1e-7..1e-9) and the projective path active (d*chi >= 128)."""
+    if model == "heisenberg_f64":
+        mpo, dtype, chi = P.mpo.heisenberg_mpo(18), "f64", 64
+    else:
+        mpo, dtype, chi = P.mpo.asep_mpo(18, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), "c128", 64
+    res = {}
+    for rec in (False, True):
+        np.random.seed(2)
+        st = {}
+        out = P.dmrg.run_dmrg(mpo, mbd=chi, tol=0.0, maxIter=6, twoSite=True, dtype=dtype, returnEntSpec=True, stats=st,
+                              recycle=rec, res_tol=1e-11)
+        res[rec] = (out[0], out[1], np.asarray(out[3]), st)
+    E0, EE0, EEs0, st0 = res[False]
+    E1, EE1, EEs1, st1 = res[True]
+    assert st1.get("n_recycled", 0) > 0 and st0.get("n_recycled", 0) == 0
+    assert abs(E1 - E0) < 1e-10 * abs(E0)
+    assert abs(EE1 - EE0) < 1e-8
+    assert np.max(np.abs(np.sort(EEs1)[::-1][:16] - np.sort(EEs0)[::-1][:16])) < 1e-8
+
+
+@pytest.mark.parametrize("direction", ["right", "left"])
+@pytest.mark.parametrize("dims", [(64, 200), (200, 64), (96, 96)])
+def test_full_rank_split(P, ctx, direction, dims):
+    """Bonds where nothing is discarded: A.B reproduces psi exactly and the side left behind is an isometry."""
+    rng = np.random.default_rng(5)
+    Dl, Dr = dims
+    d1 = d2 = 2
+    rows, cols = Dl * d1, d2 * Dr
+    k = min(rows, cols)
+    m = crand(rng, rows, cols)
+    psi = m.reshape(Dl, d1, d2, Dr).transpose(1, 2, 0, 3).reshape(-1)
+    A, B, Sn, EE, EEs = P.truncate.full_rank_split(ctx.dev(psi), (d1, d2, Dl, Dr), ctx, direction)
+    A, B = ctx.host(A), ctx.host(B)
+    Am = A.transpose(1, 0, 2).reshape(rows, k)
+    Bm = B.transpose(1, 0, 2).reshape(k, cols)
+    assert np.max(np.abs(Am @ Bm - m)) < 1e-12 * np.abs(m).max() * cols
+    iso = Am if direction == "right" else Bm.conj().T
+    assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12

@@ -9,6 +9,7 @@ which = sys.argv[1:] or ["cfg0", "cfg1", "cfg3pt"]
 out = {}
 
 SVD = os.environ.get("PDMRG_SVD", "auto")
+RECYCLE = os.environ.get("PDMRG_RECYCLE", "1") != "0"      # warm-started truncation after each bond's first visit
 
 
 def timed_sweeps(mpo, chi, dtype, n_sweeps, seed=0, two_site=True, sched=None, res_tol=None):
@@ -27,17 +28,19 @@ def timed_sweeps(mpo, chi, dtype, n_sweeps, seed=0, two_site=True, sched=None, r
     mpsL = [[ctx.dev(t) for t in mpsL[0]]]
     F = env.calc_env(mpsL[0], mpo, chi, gaugeSite=0, ctx=ctx)
     res = []
+    cache = {} if RECYCLE else None
     for s in range(n_sweeps):
         stats = {"profile": bool(os.environ.get("PDMRG_PROFILE"))}
         torch.cuda.synchronize(); t0 = time.perf_counter()
         if two_site:
-            E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, res_tol=res_tol)
+            E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, res_tol=res_tol, recycle=cache)
         else:
             E, mpsL, F, EE, EEs = dmrg.rightSweep(mpsL, mpo, F, s, ctx=ctx, stats=stats)
             E, mpsL, F, EE, EEs = dmrg.leftSweep(mpsL, mpo, F, s, ctx=ctx, stats=stats)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         res.append({"sweep": s, "sec": dt, "E": complex(E).real, "EE": float(EE), "n_matvec": stats.get("n_matvec"), "cycles": stats.get("cycles"),
-                    "t_eig": stats.get("t_eig"), "t_svd": stats.get("t_svd"), "t_env": stats.get("t_env")})
+                    "t_eig": stats.get("t_eig"), "t_svd": stats.get("t_svd"), "t_env": stats.get("t_env"),
+                    "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0)})
         print("   sweep", res[-1], flush=True)
     return {"prep_sec": t_prep, "sweeps": res}
 
@@ -58,6 +61,7 @@ if "cfg3pt1" in which:
     out["cfg3pt1"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 3, two_site=False, sched=[16, 64])
 if "cfg2" in which:
     print("cfg2: TASEP N=100 chi=1024 c128 two-site, one sweep after a [16,64,256] ramp", flush=True)
-    out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", 1, sched=[16, 64, 256])
+    out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", int(os.environ.get("PDMRG_CFG2_SWEEPS", "3")),
+                               sched=[16, 64, 256])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/run_configs.json", "w"), indent=1)
