@@ -115,7 +115,7 @@ def check_overlap(guess, vecs, E, preserveState, ctx):
 
 def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
               orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
-              fixed_cycles=None, return_device=None, plan=None, native=None):
+              fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000):
     """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
     array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise."""
     ctx = ctx or default_context()
@@ -134,7 +134,7 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     if alg == "davidson":
         vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=plan,
-                              native=native)
+                              native=native, max_cycle=max_cycle)
         E = -vals                                               # diag_tools.py:265,273
     elif alg == "exact":
         E, vecs = _eigs_exact(plan, n, nS, ctx)
