@@ -355,6 +355,8 @@ def main():
                                      "how": "198 bond steps x measured chi=%d bond step with %d Davidson cycles each and the "
                                             "warm-started truncation; upper bound (edge bonds are smaller, a converged sweep "
                                             "needs 1 cycle per bond)" % (chi, args.davidson_cycles)}
+        line["krylov"] = krylov_bandwidth(chi)
+        line["config4_matvec"] = config4_matvec()
         line["cpu_baseline"] = cpu_baseline(args)
         line["scan"] = scan_sample()
         if not args.no_full_sweep:
@@ -413,6 +415,81 @@ def bond_step(args, ctx, plan, L, R, W1, W2, chi):
         b.record()
         torch.cuda.synchronize()
         out["svd_truncate_ms_gesvd"] = a.elapsed_time(b)
+    return out
+
+
+def krylov_bandwidth(chi, m=8, reps=20):
+    """HBM roofline of the Davidson vector kernels (csrc/krylov.cu) at the headline size: vectors of
+    n = d^2 chi^2 complex128 elements, a subspace of m basis vectors + m images (2 x m x 64 MiB at chi=1024,
+    far beyond the 126 MB L2, so every pass streams from HBM).  achieved = ALGORITHMIC bytes (each vector
+    touched once per pass) / CUDA-event time; peak = MEASURED_PEAKS.json hbm_gbs (copy bandwidth)."""
+    import torch
+    from pydmrg_b200 import device as D
+    n = 4 * chi * chi
+    B = 16 * n
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "MEASURED_PEAKS.json:hbm_gbs"
+    except Exception:
+        peak, src = 6500.0, "fallback (B200_PROFILING.md copy bandwidth)"
+    ops = D.VecOps(D.C128, n, torch.device("cuda"))
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    XS = torch.randn(m, n, dtype=torch.complex128, device="cuda", generator=g)
+    AX = torch.randn(m, n, dtype=torch.complex128, device="cuda", generator=g)
+    y = torch.randn(n, dtype=torch.complex128, device="cuda", generator=g)
+    r = torch.empty_like(y)
+    coef = (np.arange(1, m + 1) / m).astype(np.complex128)
+    cdev = ops.dots(XS, m, y).clone()
+    cases = {
+        "dots (m inner products <X_i|y>)": (lambda: ops.dots(XS, m, y), (m + 1) * B),
+        "combine (Ritz vector = sum c_i X_i)": (lambda: ops.combine(coef, XS, m, r), (m + 1) * B),
+        "residual (r = sum v_i (AX_i - e X_i), fused norm)": (lambda: ops.residual(coef, 0.5, XS, AX, m, r), (2 * m + 1) * B),
+        "project (r -= sum c_i X_i, fused norm)": (lambda: ops.project(XS, m, cdev, r), (m + 2) * B),
+        "normalize": (lambda: ops.normalize(y, ops.norm2, r), 2 * B),
+    }
+    out = {"n": n, "m": m, "peak_gbs": peak, "peak_source": src, "kernels": {}}
+    for name, (f, nbytes) in cases.items():
+        for _ in range(3):
+            f()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = nbytes / (ms * 1e-3) * 1e-9
+        out["kernels"][name] = {"ms": ms, "bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak}
+    return out
+
+
+def config4_matvec(chi=2048, reps=10):
+    """BASELINE configs[4] probe: the Heisenberg (w=5, real f64) two-site mat-vec at chi=2048 on ONE GPU
+    (operands 2 x 168 MB blocks + 2 x 671 MB intermediates: the N=200 chain's 34 GB of blocks fit one B200)."""
+    import torch
+    from pydmrg_b200 import core, device as D, mpo as M
+    ctx = core.Context("f64")
+    W1, W2 = M.heisenberg_mpo(6)[0][2:4]
+    Wc = D.combine_twosite(W1, W2, np.float64)
+    w = W1.shape[0]
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.float64, device="cuda", generator=g)
+    L, R, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(4 * chi * chi)
+    y = torch.empty_like(x)
+    plan = D.HeffPlan(D.F64, 4, chi, chi, [(L, Wc, R)], ctx.ws)
+    for _ in range(3):
+        plan.apply(x, y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        plan.apply(x, y)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * (2 * 4 * w * chi ** 3 + 2 * 8 * w * w * chi ** 2)
+    out = {"workload": "Heisenberg w=%d f64 two-site H_eff mat-vec, chi=%d" % (w, chi), "ms": ms,
+           "dense_flops": flops, "tflops_dense_count": flops / (ms * 1e-3) * 1e-12,
+           "executed_gemm_tflops": plan.flops_gemm / (ms * 1e-3) * 1e-12}
+    plan.close()
     return out
 
 

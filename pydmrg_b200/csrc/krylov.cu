@@ -15,6 +15,7 @@ namespace {
 constexpr int VT = 256;        // threads per block
 constexpr int MAXM = 16;       // basis vectors handled per pass
 constexpr int MAX_BLOCKS = 148 * 4;
+constexpr int MAX_DOT_PARTIALS = 4736;   // slice streams of the dots kernel (148 SMs x 8 blocks x up to 4 slices)
 
 struct Coefs {
   double re[2 * MAXM + 2];
@@ -48,50 +49,78 @@ __device__ __forceinline__ void block_reduce_store(double (&vals)[NV], int nv, d
   }
 }
 
-// out[i] = sum over blocks of partial[b*nv + i]   (single block, ordered)
+// out[i] = sum over blocks of partial[b*nv + i]   (single block; warp w reduces values w, w+8, ...: every
+// lane adds its blocks in a fixed order and the lanes are combined by a fixed shuffle tree -> reproducible)
 __global__ void __launch_bounds__(VT) final_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv,
                                                           double* __restrict__ out) {
-  __shared__ double sm[VT];
-  for (int i = 0; i < nv; ++i) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < nv; i += VT / 32) {
     double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += VT) s += partial[(size_t)b * nv + i];
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = VT / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[i] = sm[0];
-    __syncthreads();
+    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * nv + i];
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
   }
 }
 
+// out-of-register formulation: the 8 warps of a block split into P = 2^k <= min(m, 8) vector groups and
+// S = 8 / P element slices.  Warp (g, s) walks the chunks of slice stream (block, s) and accumulates
+// <X_i|y> for i = g, g + P (< m <= 16): two complex accumulators per lane instead of 2*m, so eight blocks
+// stay resident per SM and every lane keeps four independent 16-byte loads of X in flight; the P warps of a
+// slice read the same y chunk, which is served by L1 after the first.  partial[(block*S + s)*nv + comp].
 template <bool CPLX>
 __global__ void __launch_bounds__(VT)
-dots_kernel(long long n, int m, const double* __restrict__ X, long long stride, const double* __restrict__ y,
+dots_kernel(long long n, int m, int P, const double* __restrict__ X, long long stride, const double* __restrict__ y,
             double* __restrict__ partial) {
-  double acc[2 * MAXM];
-#pragma unroll
-  for (int i = 0; i < 2 * MAXM; ++i) acc[i] = 0.0;
-  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+  constexpr int U = 4;                                   // elements per lane per chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = (VT / 32) / P;
+  const int g = warp % P, sl = warp / P;
+  const int i0 = g, i1 = g + P;                          // i1 may be >= m (then unused)
+  const bool two = i1 < m;
+  double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+  const long long chunk = 32 * U;
+  const long long nchunks = (n + chunk - 1) / chunk;
+  for (long long q = (long long)blockIdx.x * S + sl; q < nchunks; q += (long long)gridDim.x * S) {
+    const long long base = q * chunk + lane;
     if (CPLX) {
-      const double2 yv = reinterpret_cast<const double2*>(y)[e];
+      double2 yv[U], x0[U], x1[U];
 #pragma unroll
-      for (int i = 0; i < MAXM; ++i) {
-        if (i < m) {
-          const double2 xv = reinterpret_cast<const double2*>(X + 2 * i * stride)[e];
-          acc[2 * i] = fma(xv.x, yv.x, acc[2 * i]); acc[2 * i] = fma(xv.y, yv.y, acc[2 * i]);
-          acc[2 * i + 1] = fma(xv.x, yv.y, acc[2 * i + 1]); acc[2 * i + 1] = fma(-xv.y, yv.x, acc[2 * i + 1]);
-        }
+      for (int u = 0; u < U; ++u) {
+        const long long e = base + 32 * u;
+        const bool ok = e < n;
+        yv[u] = ok ? reinterpret_cast<const double2*>(y)[e] : make_double2(0.0, 0.0);
+        x0[u] = ok ? reinterpret_cast<const double2*>(X + 2 * i0 * stride)[e] : make_double2(0.0, 0.0);
+        x1[u] = (ok && two) ? reinterpret_cast<const double2*>(X + 2 * i1 * stride)[e] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a0r = fma(x0[u].x, yv[u].x, a0r); a0r = fma(x0[u].y, yv[u].y, a0r);
+        a0i = fma(x0[u].x, yv[u].y, a0i); a0i = fma(-x0[u].y, yv[u].x, a0i);
+        a1r = fma(x1[u].x, yv[u].x, a1r); a1r = fma(x1[u].y, yv[u].y, a1r);
+        a1i = fma(x1[u].x, yv[u].y, a1i); a1i = fma(-x1[u].y, yv[u].x, a1i);
       }
     } else {
-      const double yv = y[e];
+      double yv[U], x0[U], x1[U];
 #pragma unroll
-      for (int i = 0; i < MAXM; ++i)
-        if (i < m) acc[i] = fma(X[i * stride + e], yv, acc[i]);
+      for (int u = 0; u < U; ++u) {
+        const long long e = base + 32 * u;
+        const bool ok = e < n;
+        yv[u] = ok ? y[e] : 0.0;
+        x0[u] = ok ? X[i0 * stride + e] : 0.0;
+        x1[u] = (ok && two) ? X[i1 * stride + e] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { a0r = fma(x0[u], yv[u], a0r); a1r = fma(x1[u], yv[u], a1r); }
     }
   }
-  block_reduce_store<2 * MAXM>(acc, CPLX ? 2 * m : m, partial);
+  a0r = warp_sum(a0r); a0i = warp_sum(a0i); a1r = warp_sum(a1r); a1i = warp_sum(a1i);
+  if (lane == 0) {
+    constexpr int E = CPLX ? 2 : 1;
+    double* dst = partial + ((size_t)blockIdx.x * S + sl) * (E * m);
+    dst[E * i0] = a0r;
+    if (CPLX) dst[E * i0 + 1] = a0i;
+    if (two) { dst[E * i1] = a1r; if (CPLX) dst[E * i1 + 1] = a1i; }
+  }
 }
 
 template <bool CPLX>
@@ -149,12 +178,16 @@ __global__ void __launch_bounds__(VT)
 project_kernel(long long n, int m, const double* __restrict__ X, long long stride, const double* __restrict__ cdev,
                const double* __restrict__ scale, double* __restrict__ r, double* __restrict__ partial) {
   const double s = scale ? (1.0 / sqrt(scale[0])) : 1.0;
+  __shared__ double csh[2 * MAXM];                 // the coefficients come from a device-side dots result
+  if ((int)threadIdx.x < (CPLX ? 2 : 1) * m) csh[threadIdx.x] = -cdev[threadIdx.x];
+  __syncthreads();
   double nrm[1] = {0.0};
   for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
     if (CPLX) {
       double2 res = reinterpret_cast<double2*>(r)[e];
+#pragma unroll 8
       for (int i = 0; i < m; ++i) {
-        const double2 ci = make_double2(-cdev[2 * i], -cdev[2 * i + 1]);
+        const double2 ci = make_double2(csh[2 * i], csh[2 * i + 1]);
         cfma(res, ci, reinterpret_cast<const double2*>(X + 2 * i * stride)[e]);
       }
       res.x *= s; res.y *= s;
@@ -162,7 +195,8 @@ project_kernel(long long n, int m, const double* __restrict__ X, long long strid
       nrm[0] = fma(res.x, res.x, nrm[0]); nrm[0] = fma(res.y, res.y, nrm[0]);
     } else {
       double res = r[e];
-      for (int i = 0; i < m; ++i) res = fma(-cdev[i], X[i * stride + e], res);
+#pragma unroll 8
+      for (int i = 0; i < m; ++i) res = fma(csh[i], X[i * stride + e], res);
       res *= s;
       r[e] = res;
       nrm[0] = fma(res, res, nrm[0]);
@@ -194,7 +228,7 @@ using namespace pdmrg;
 
 extern "C" size_t pdmrg_vec_scratch_bytes(int m) {
   (void)m;
-  return (size_t)MAX_BLOCKS * 2 * MAXM * sizeof(double) + 256;
+  return (size_t)MAX_DOT_PARTIALS * 2 * MAXM * sizeof(double) + 256;
 }
 
 extern "C" int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long long stride, const void* y,
@@ -204,16 +238,24 @@ extern "C" int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long
   PDMRG_REQUIRE(n > 0 && m >= 0, "pdmrg_vec_dots: bad extents");
   const bool cplx = dtype == PDMRG_C128;
   const int E = cplx ? 2 : 1;
-  const int grid = vec_grid(n);
   double* partial = static_cast<double*>(scratch);
   for (int i0 = 0; i0 < m; i0 += MAXM) {
     const int mm = (m - i0) < MAXM ? (m - i0) : MAXM;
     const double* Xp = static_cast<const double*>(X) + (size_t)E * i0 * stride;
-    if (cplx) dots_kernel<true><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, (const double*)y, partial);
-    else dots_kernel<false><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, (const double*)y, partial);
+    int P = 1;
+    while (2 * P <= mm && 2 * P <= VT / 32) P *= 2;
+    const int S = (VT / 32) / P;
+    const long long nchunks = (n + 127) / 128;
+    long long want = (nchunks + S - 1) / S;
+    long long cap = (long long)num_sms() * 8;
+    if (cap * S > MAX_DOT_PARTIALS) cap = MAX_DOT_PARTIALS / S;
+    if (want > cap) want = cap;
+    const int grid = (int)(want < 1 ? 1 : want);
+    if (cplx) dots_kernel<true><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial);
+    else dots_kernel<false><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial);
     PDMRG_CHECK_LAUNCH();
     // complex: partial holds (re,im) pairs -> out is interleaved complex
-    final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, E * mm, static_cast<double*>(out_dev) + E * i0);
+    final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid * S, E * mm, static_cast<double*>(out_dev) + E * i0);
     PDMRG_CHECK_LAUNCH();
     count_launch(2);
   }
