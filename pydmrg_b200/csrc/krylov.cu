@@ -55,9 +55,16 @@ __global__ void __launch_bounds__(VT) final_reduce_kernel(const double* __restri
                                                           double* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = warp; i < nv; i += VT / 32) {
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * nv + i];
-    s = warp_sum(s);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // four independent chains hide the load latency
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {
+      s0 += partial[(size_t)b * nv + i];
+      s1 += partial[(size_t)(b + 32) * nv + i];
+      s2 += partial[(size_t)(b + 64) * nv + i];
+      s3 += partial[(size_t)(b + 96) * nv + i];
+    }
+    for (; b < nblocks; b += 32) s0 += partial[(size_t)b * nv + i];
+    double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) out[i] = s;
   }
 }
