@@ -185,6 +185,9 @@ int pdmrg_vec_project(int dtype, long long n, int m, const void* X, long long st
 /* out = in * (norm2_dev[0])^-1/2  (out may alias in) */
 int pdmrg_vec_normalize(int dtype, long long n, const void* in, const double* norm2_dev,
                         void* out, void* stream);
+/* Scratch for the reductions above.  Its last 256 bytes hold the ticket of the fused second reduction
+ * stage: the buffer must be ZERO-filled once before first use (the kernels leave the ticket at zero), and
+ * one scratch buffer must not be shared by kernels running concurrently on different streams. */
 size_t pdmrg_vec_scratch_bytes(int m);
 
 /* ---- the whole local eigensolve behind one call (K + D: tools/la_tools.py:402-557 as driven by

@@ -317,17 +317,23 @@ extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, cons
     PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));                       // D2H #2 of the cycle
     last_res = 0.0;
     trial.clear();
+    std::vector<int> keep;
     for (int k = 0; k < nr; ++k) {
       const double dx2 = pin[2 * k], px2 = pin[2 * k + 1];
       if (std::sqrt(std::max(dx2, 0.0)) > last_res) last_res = std::sqrt(std::max(dx2, 0.0));
-      if (dx2 > thresh2 && px2 > lindep) {                                  // la_tools.py:505-537
-        if (normalise_from(rv(k), norms + 2 * k + 1)) return 1;
-        trial.push_back(rv(k));
-      }
+      if (dx2 > thresh2 && px2 > lindep) keep.push_back(k);                 // la_tools.py:505-537
     }
-    if (trial.empty()) { ++cyc; break; }                                    // la_tools.py:539-541
+    if (keep.empty()) { ++cyc; break; }                                     // la_tools.py:539-541
     if (fixed_cycles > 0 && cyc + 1 >= fixed_cycles) { ++cyc; break; }
     fresh = space + nroots > ms;                                            // la_tools.py:544
+    if (!fresh) {
+      for (int k : keep) {
+        // a single new direction is normalised straight into its basis slot (no copy next cycle)
+        double* dst = keep.size() == 1 ? xs(space) : rv(k);
+        if (pdmrg_vec_normalize(dtype, n, rv(k), norms + 2 * k + 1, dst, stream)) return 1;
+        trial.push_back(dst);
+      }
+    }
     if (fresh) {
       x0v.clear();
       for (int k = 0; k < nr; ++k) {

@@ -49,24 +49,36 @@ __device__ __forceinline__ void block_reduce_store(double (&vals)[NV], int nv, d
   }
 }
 
-// out[i] = sum over blocks of partial[b*nv + i]   (single block; warp w reduces values w, w+8, ...: every
-// lane adds its blocks in a fixed order and the lanes are combined by a fixed shuffle tree -> reproducible)
-__global__ void __launch_bounds__(VT) final_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv,
-                                                          double* __restrict__ out) {
+// Fused second stage of the ordered two-stage reductions: every block publishes its partials, takes a
+// ticket, and the block that draws the last ticket sums ALL partials in a fixed order (warp w reduces values
+// w, w+8, ...; every lane adds its rows in order, four independent chains, then a fixed shuffle tree) -- the
+// result does not depend on which block happens to be last, so it is bit-reproducible, and the separate
+// one-block kernel launch is gone (the Davidson loop at small bond dimension is launch-latency bound).
+// `ticket` lives in the last 256 bytes of the caller's scratch buffer: zero before first use, left at zero.
+__device__ __forceinline__ void last_block_reduce(const double* partial, int nrows, int nv, double* __restrict__ out,
+                                                  unsigned int* ticket) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = warp; i < nv; i += VT / 32) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // four independent chains hide the load latency
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int b = lane;
-    for (; b + 96 < nblocks; b += 128) {
-      s0 += partial[(size_t)b * nv + i];
-      s1 += partial[(size_t)(b + 32) * nv + i];
-      s2 += partial[(size_t)(b + 64) * nv + i];
-      s3 += partial[(size_t)(b + 96) * nv + i];
+    for (; b + 96 < nrows; b += 128) {
+      s0 += __ldcg(partial + (size_t)b * nv + i);
+      s1 += __ldcg(partial + (size_t)(b + 32) * nv + i);
+      s2 += __ldcg(partial + (size_t)(b + 64) * nv + i);
+      s3 += __ldcg(partial + (size_t)(b + 96) * nv + i);
     }
-    for (; b < nblocks; b += 32) s0 += partial[(size_t)b * nv + i];
-    double s = warp_sum((s0 + s1) + (s2 + s3));
+    for (; b < nrows; b += 32) s0 += __ldcg(partial + (size_t)b * nv + i);
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) out[i] = s;
   }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // out-of-register formulation: the 8 warps of a block split into P = 2^k <= min(m, 8) vector groups and
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(VT) final_reduce_kernel(const double* __restri
 template <bool CPLX>
 __global__ void __launch_bounds__(VT)
 dots_kernel(long long n, int m, int P, const double* __restrict__ X, long long stride, const double* __restrict__ y,
-            double* __restrict__ partial) {
+            double* partial, double* __restrict__ out, unsigned int* ticket) {
   constexpr int U = 4;                                   // elements per lane per chunk
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int S = (VT / 32) / P;
@@ -128,6 +140,7 @@ dots_kernel(long long n, int m, int P, const double* __restrict__ X, long long s
     if (CPLX) dst[E * i0 + 1] = a0i;
     if (two) { dst[E * i1] = a1r; if (CPLX) dst[E * i1 + 1] = a1i; }
   }
+  last_block_reduce(partial, gridDim.x * S, (CPLX ? 2 : 1) * m, out, ticket);
 }
 
 template <bool CPLX>
@@ -152,7 +165,8 @@ combine_kernel(long long n, int m, Coefs c, const double* __restrict__ X, long l
 template <bool CPLX>
 __global__ void __launch_bounds__(VT)
 residual_kernel(long long n, int m, Coefs c, const double* __restrict__ XS, const double* __restrict__ AX,
-                long long stride, double* __restrict__ r, int accumulate, double* __restrict__ partial) {
+                long long stride, double* __restrict__ r, int accumulate, double* partial, double* __restrict__ norm2_out,
+                unsigned int* ticket) {
   double nrm[1] = {0.0};
   for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
     if (CPLX) {
@@ -177,13 +191,15 @@ residual_kernel(long long n, int m, Coefs c, const double* __restrict__ XS, cons
     }
   }
   block_reduce_store<1>(nrm, 1, partial);
+  last_block_reduce(partial, gridDim.x, 1, norm2_out, ticket);
 }
 
 // r = (r - sum_i c_i X_i) * s,  s = (1.0 / sqrt(scale[0])) if scale given on the LAST pass
 template <bool CPLX>
 __global__ void __launch_bounds__(VT)
 project_kernel(long long n, int m, const double* __restrict__ X, long long stride, const double* __restrict__ cdev,
-               const double* __restrict__ scale, double* __restrict__ r, double* __restrict__ partial) {
+               const double* __restrict__ scale, double* __restrict__ r, double* partial, double* __restrict__ norm2_out,
+               unsigned int* ticket) {
   const double s = scale ? (1.0 / sqrt(scale[0])) : 1.0;
   __shared__ double csh[2 * MAXM];                 // the coefficients come from a device-side dots result
   if ((int)threadIdx.x < (CPLX ? 2 : 1) * m) csh[threadIdx.x] = -cdev[threadIdx.x];
@@ -210,6 +226,7 @@ project_kernel(long long n, int m, const double* __restrict__ X, long long strid
     }
   }
   block_reduce_store<1>(nrm, 1, partial);
+  last_block_reduce(partial, gridDim.x, 1, norm2_out, ticket);
 }
 
 template <bool CPLX>
@@ -238,6 +255,11 @@ extern "C" size_t pdmrg_vec_scratch_bytes(int m) {
   return (size_t)MAX_DOT_PARTIALS * 2 * MAXM * sizeof(double) + 256;
 }
 
+// the reduction ticket lives in the last 256 bytes of the vector scratch (ZERO before first use)
+static unsigned int* ticket_of(void* scratch) {
+  return reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(scratch) + (size_t)MAX_DOT_PARTIALS * 2 * MAXM * sizeof(double));
+}
+
 extern "C" int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long long stride, const void* y,
                               void* out_dev, void* scratch, size_t scratch_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -258,13 +280,12 @@ extern "C" int pdmrg_vec_dots(int dtype, long long n, int m, const void* X, long
     if (cap * S > MAX_DOT_PARTIALS) cap = MAX_DOT_PARTIALS / S;
     if (want > cap) want = cap;
     const int grid = (int)(want < 1 ? 1 : want);
-    if (cplx) dots_kernel<true><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial);
-    else dots_kernel<false><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial);
-    PDMRG_CHECK_LAUNCH();
     // complex: partial holds (re,im) pairs -> out is interleaved complex
-    final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid * S, E * mm, static_cast<double*>(out_dev) + E * i0);
+    double* outp = static_cast<double*>(out_dev) + E * i0;
+    if (cplx) dots_kernel<true><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial, outp, ticket_of(scratch));
+    else dots_kernel<false><<<grid, VT, 0, stream>>>(n, mm, P, Xp, stride, (const double*)y, partial, outp, ticket_of(scratch));
     PDMRG_CHECK_LAUNCH();
-    count_launch(2);
+    count_launch();
   }
   return 0;
 }
@@ -318,14 +339,11 @@ extern "C" int pdmrg_davidson_residual(int dtype, long long n, int m, const void
     c.im[2 * MAXM] = cplx ? eh[1] : 0.0;
     const double* XSp = static_cast<const double*>(XS) + (size_t)E * i0 * stride;
     const double* AXp = static_cast<const double*>(AX) + (size_t)E * i0 * stride;
-    if (cplx) residual_kernel<true><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial);
-    else residual_kernel<false><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial);
+    if (cplx) residual_kernel<true><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial, norm2_dev, ticket_of(scratch));
+    else residual_kernel<false><<<grid, VT, 0, stream>>>(n, mm, c, XSp, AXp, stride, (double*)r, i0 > 0, partial, norm2_dev, ticket_of(scratch));
     PDMRG_CHECK_LAUNCH();
     count_launch();
   }
-  final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, 1, norm2_dev);
-  PDMRG_CHECK_LAUNCH();
-  count_launch();
   return 0;
 }
 
@@ -338,12 +356,10 @@ extern "C" int pdmrg_vec_project(int dtype, long long n, int m, const void* X, l
   const bool cplx = dtype == PDMRG_C128;
   const int grid = vec_grid(n);
   double* partial = static_cast<double*>(scratch);
-  if (cplx) project_kernel<true><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial);
-  else project_kernel<false><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial);
+  if (cplx) project_kernel<true><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial, norm2_dev, ticket_of(scratch));
+  else project_kernel<false><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial, norm2_dev, ticket_of(scratch));
   PDMRG_CHECK_LAUNCH();
-  final_reduce_kernel<<<1, VT, 0, stream>>>(partial, grid, 1, norm2_dev);
-  PDMRG_CHECK_LAUNCH();
-  count_launch(2);
+  count_launch();
   return 0;
 }
 

@@ -246,7 +246,7 @@ class VecOps:
         self.dt = torch_dtype(code)
         self.npdt = np_dtype(code)
         nb = int(lib.pdmrg_vec_scratch_bytes(64))
-        self.scratch = torch.empty(nb, dtype=torch.uint8, device=device)
+        self.scratch = torch.zeros(nb, dtype=torch.uint8, device=device)      # holds the reduction ticket: must start at zero
         self.norm2 = torch.zeros(2, dtype=torch.float64, device=device)
         self.coefs = torch.zeros(128, dtype=self.dt, device=device)
 
