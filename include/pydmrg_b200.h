@@ -244,10 +244,14 @@ int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X, void* Ut,
  *   vectors of that window (sorted by decreasing weight);  S[i] = ||Ct[i, :]||.
  * X1 (a x c) and X2 = X1^T (c x a) are row-major and read-only, Wt (K x c) holds the previous basis
  * (k kept rows, then K-k spare rows, ordered by weight).  Needs K <= min(a, c).  The caller keeps rows
- * [0, k).  info_dev receives the last cuSOLVER info. */
+ * [0, k).  method 0: Householder QR (cuSOLVER geqrf/ungqr); method 1: Cholesky-QR2 on the row-normalised T
+ * (DMMA GEMMs + potrf + trsm; same triangular structure, ~2x faster, valid while the normalised rows are
+ * not numerically dependent).  S has K + 2 entries: S[K] = ||P1 P1^H - I||_F^2 after the first Cholesky
+ * pass (the caller must fall back to method 0 when it is not << 1), S[K+1] = number of non-zero cuSOLVER
+ * infos.  info_dev: int[4] = {geqrf/ungqr, potrf pass 1, potrf pass 2, window eigensolver}. */
 size_t pdmrg_recycle_basis_workspace_bytes(int dtype, int a, int c, int K, int k, int b);
-int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, const void* X1, const void* X2,
-                        const void* Wt, void* Pt, void* Ct, double* S, void* workspace,
+int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, int method, const void* X1,
+                        const void* X2, const void* Wt, void* Pt, void* Ct, double* S, void* workspace,
                         size_t workspace_bytes, int* info_dev, void* stream);
 /* T1 (dmrg.py:64-76): eigen-decomposition of a Hermitian (n x n) row-major matrix, in place:
  * on exit row i of `a` is the i-th eigenvector (ascending eigenvalues in w). */

@@ -78,7 +78,7 @@ def _load():
         "pdmrg_left_basis_workspace_bytes": (sz, [i, i, i]),
         "pdmrg_left_basis": (i, [i, i, i, i, vp, vp, vp, vp, sz, vp, vp]),
         "pdmrg_recycle_basis_workspace_bytes": (sz, [i, i, i, i, i, i]),
-        "pdmrg_recycle_basis": (i, [i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
+        "pdmrg_recycle_basis": (i, [i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
         "pdmrg_heevd_workspace_bytes": (sz, [i, i]),
         "pdmrg_heevd": (i, [i, i, vp, vp, vp, sz, vp, vp]),
     }

@@ -6,6 +6,7 @@
 //   a^T = Uc S VTc   =>   a = VTc^T S Uc^T,   row-major U = VTc buffer, row-major Vh = Uc buffer.
 #include "common.cuh"
 
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <dlfcn.h>
 #include <mutex>
@@ -45,7 +46,27 @@ struct Solver {
   PDMRG_SOLVER_FN(cusolverDnDorgqr_bufferSize)
   PDMRG_SOLVER_FN(cusolverDnZungqr)
   PDMRG_SOLVER_FN(cusolverDnDorgqr)
+  PDMRG_SOLVER_FN(cusolverDnZpotrf_bufferSize)
+  PDMRG_SOLVER_FN(cusolverDnDpotrf_bufferSize)
+  PDMRG_SOLVER_FN(cusolverDnZpotrf)
+  PDMRG_SOLVER_FN(cusolverDnDpotrf)
+  PDMRG_SOLVER_FN(cusolverDnCreateSyevjInfo)
+  PDMRG_SOLVER_FN(cusolverDnXsyevjSetTolerance)
+  PDMRG_SOLVER_FN(cusolverDnXsyevjSetMaxSweeps)
+  PDMRG_SOLVER_FN(cusolverDnXsyevjSetSortEig)
+  PDMRG_SOLVER_FN(cusolverDnZheevj_bufferSize)
+  PDMRG_SOLVER_FN(cusolverDnDsyevj_bufferSize)
+  PDMRG_SOLVER_FN(cusolverDnZheevj)
+  PDMRG_SOLVER_FN(cusolverDnDsyevj)
 #undef PDMRG_SOLVER_FN
+  syevjInfo_t evj = nullptr;
+  // cuBLAS (triangular solves of the Cholesky-QR route), dlopen'ed like cuSOLVER
+  void* blas_lib = nullptr;
+  cublasHandle_t blas = nullptr;
+  decltype(&cublasCreate_v2) p_cublasCreate = nullptr;
+  decltype(&cublasSetStream_v2) p_cublasSetStream = nullptr;
+  decltype(&cublasZtrsm_v2) p_cublasZtrsm = nullptr;
+  decltype(&cublasDtrsm_v2) p_cublasDtrsm = nullptr;
 };
 
 Solver* get_solver() {
@@ -89,13 +110,43 @@ Solver* get_solver() {
     PDMRG_LOAD(cusolverDnDorgqr_bufferSize)
     PDMRG_LOAD(cusolverDnZungqr)
     PDMRG_LOAD(cusolverDnDorgqr)
+    PDMRG_LOAD(cusolverDnZpotrf_bufferSize)
+    PDMRG_LOAD(cusolverDnDpotrf_bufferSize)
+    PDMRG_LOAD(cusolverDnZpotrf)
+    PDMRG_LOAD(cusolverDnDpotrf)
+    PDMRG_LOAD(cusolverDnCreateSyevjInfo)
+    PDMRG_LOAD(cusolverDnXsyevjSetTolerance)
+    PDMRG_LOAD(cusolverDnXsyevjSetMaxSweeps)
+    PDMRG_LOAD(cusolverDnXsyevjSetSortEig)
+    PDMRG_LOAD(cusolverDnZheevj_bufferSize)
+    PDMRG_LOAD(cusolverDnDsyevj_bufferSize)
+    PDMRG_LOAD(cusolverDnZheevj)
+    PDMRG_LOAD(cusolverDnDsyevj)
 #undef PDMRG_LOAD
     if (!all) return;
+    {
+      const char* bn[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+      for (const char* n : bn) {
+        s.blas_lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (s.blas_lib) break;
+      }
+      if (!s.blas_lib) { set_error("cannot dlopen libcublas: %s", dlerror()); return; }
+      s.p_cublasCreate = reinterpret_cast<decltype(&cublasCreate_v2)>(dlsym(s.blas_lib, "cublasCreate_v2"));
+      s.p_cublasSetStream = reinterpret_cast<decltype(&cublasSetStream_v2)>(dlsym(s.blas_lib, "cublasSetStream_v2"));
+      s.p_cublasZtrsm = reinterpret_cast<decltype(&cublasZtrsm_v2)>(dlsym(s.blas_lib, "cublasZtrsm_v2"));
+      s.p_cublasDtrsm = reinterpret_cast<decltype(&cublasDtrsm_v2)>(dlsym(s.blas_lib, "cublasDtrsm_v2"));
+      if (!s.p_cublasCreate || !s.p_cublasSetStream || !s.p_cublasZtrsm || !s.p_cublasDtrsm) { set_error("cublas symbols missing"); return; }
+      if (s.p_cublasCreate(&s.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return; }
+    }
     if (s.p_cusolverDnCreate(&s.handle) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return; }
     if (s.p_cusolverDnCreateGesvdjInfo(&s.jinfo) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateGesvdjInfo failed"); return; }
     s.p_cusolverDnXgesvdjSetTolerance(s.jinfo, 1e-15);
     s.p_cusolverDnXgesvdjSetMaxSweeps(s.jinfo, 100);
     s.p_cusolverDnXgesvdjSetSortEig(s.jinfo, 1);
+    if (s.p_cusolverDnCreateSyevjInfo(&s.evj) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateSyevjInfo failed"); return; }
+    s.p_cusolverDnXsyevjSetTolerance(s.evj, 1e-15);
+    s.p_cusolverDnXsyevjSetMaxSweeps(s.evj, 100);
+    s.p_cusolverDnXsyevjSetSortEig(s.evj, 1);
     ok = true;
   });
   return ok ? &s : nullptr;
@@ -553,10 +604,12 @@ extern "C" int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X
 namespace pdmrg {
 namespace {
 
+constexpr int RECYCLE_JACOBI_MAX = 160;    // window sizes up to this use cuSOLVER's one-kernel Jacobi eigensolver
+
 struct RecycleLayout {
-  size_t tau, H, lam, Tw, lwork_bytes;
+  size_t tau, H, lam, Tw, G, lwork_bytes;
   int lwork_elems;
-  size_t total() const { return tau + H + lam + Tw + lwork_bytes; }
+  size_t total() const { return tau + H + lam + Tw + G + lwork_bytes; }
 };
 
 int recycle_layout(Solver* s, int dtype, int a, int c, int K, int w, RecycleLayout* l) {
@@ -566,20 +619,29 @@ int recycle_layout(Solver* s, int dtype, int a, int c, int K, int w, RecycleLayo
   l->H = align_up((size_t)w * w * eb, 256);
   l->lam = align_up((size_t)w * 8, 256);
   l->Tw = align_up((size_t)w * (size_t)(a > c ? a : c) * eb, 256);
-  int lw_e = 0, lw_q = 0, lw_g = 0;
+  l->G = align_up((size_t)K * K * eb, 256);
+  int lw_e = 0, lw_q = 0, lw_g = 0, lw_p = 0, lw_j = 0;
   cusolverStatus_t st;
   if (dtype == PDMRG_C128) {
     st = s->p_cusolverDnZheevd_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_e);
     if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnZgeqrf_bufferSize(s->handle, a, K, nullptr, a, &lw_q);
     if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnZungqr_bufferSize(s->handle, a, K, K, nullptr, a, nullptr, &lw_g);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnZpotrf_bufferSize(s->handle, CUBLAS_FILL_MODE_LOWER, K, nullptr, K, &lw_p);
+    if (st == CUSOLVER_STATUS_SUCCESS && w <= RECYCLE_JACOBI_MAX)
+      st = s->p_cusolverDnZheevj_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_j, s->evj);
   } else {
     st = s->p_cusolverDnDsyevd_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_e);
     if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnDgeqrf_bufferSize(s->handle, a, K, nullptr, a, &lw_q);
     if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnDorgqr_bufferSize(s->handle, a, K, K, nullptr, a, nullptr, &lw_g);
+    if (st == CUSOLVER_STATUS_SUCCESS) st = s->p_cusolverDnDpotrf_bufferSize(s->handle, CUBLAS_FILL_MODE_LOWER, K, nullptr, K, &lw_p);
+    if (st == CUSOLVER_STATUS_SUCCESS && w <= RECYCLE_JACOBI_MAX)
+      st = s->p_cusolverDnDsyevj_bufferSize(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, nullptr, w, nullptr, &lw_j, s->evj);
   }
   if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolver bufferSize (recycle) failed (%d)", (int)st); return 1; }
   int lw = lw_e > lw_q ? lw_e : lw_q;
   if (lw_g > lw) lw = lw_g;
+  if (lw_p > lw) lw = lw_p;
+  if (lw_j > lw) lw = lw_j;
   l->lwork_elems = lw;
   l->lwork_bytes = align_up((size_t)lw * eb, 256) + 256;
   return 0;
@@ -601,6 +663,106 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const double* __restrict_
   if (threadIdx.x == 0) out[blockIdx.x] = sqrt(sm[0]);
 }
 
+// Row normalisation before the Cholesky-QR passes; one block per row, norms[] = row norms (row_norm_kernel).
+// Rows whose norm is below 1e-12 of the largest are numerical noise (the wave-function has no weight there:
+// rank-deficient cuts, e.g. product-like states at large chi).  Their computed direction is rounding error
+// confined to the few rows of psi that carry weight, so hundreds of them are numerically DEPENDENT and would
+// break the Cholesky factorisation; any orthonormal completion is as good as any other for such rows, so
+// they are replaced by reproducible pseudo-random vectors (splitmix64 of (row, element)) before normalising.
+template <int E>
+__global__ void __launch_bounds__(256) row_normalize_kernel(double* __restrict__ M, long long len, const double* __restrict__ norms,
+                                                            int nrows) {
+  __shared__ double sm[256];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < nrows; i += 256) mx = fmax(mx, norms[i]);
+  sm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  mx = sm[0];
+  __syncthreads();
+  double* row = M + (size_t)blockIdx.x * len * E;
+  const double nrm = norms[blockIdx.x];
+  if (nrm > 1e-12 * mx) {
+    const double sc = 1.0 / nrm;
+    for (long long i = threadIdx.x; i < len * E; i += 256) row[i] *= sc;
+    return;
+  }
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < len * E; i += 256) {
+    unsigned long long z = ((unsigned long long)blockIdx.x << 32) + (unsigned long long)i + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const double v = (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;     // uniform in [-1, 1)
+    row[i] = v;
+    s = fma(v, v, s);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double sc = 1.0 / sqrt(sm[0]);
+  for (long long i = threadIdx.x; i < len * E; i += 256) row[i] *= sc;
+}
+
+// out[0] += || G - I ||_F^2 over this block's share of the row-major (K x K) matrix G
+template <int E>
+__global__ void __launch_bounds__(256) gram_defect_kernel(const double* __restrict__ G, int K, double* __restrict__ out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  const long long tot = (long long)K * K;
+  for (long long t = blockIdx.x * 256ll + threadIdx.x; t < tot; t += (long long)gridDim.x * 256) {
+    const int i = (int)(t / K), j = (int)(t - (long long)i * K);
+    double re = G[(size_t)E * t] - (i == j ? 1.0 : 0.0);
+    double im = E == 2 ? G[(size_t)E * t + 1] : 0.0;
+    s = fma(re, re, s); s = fma(im, im, s);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, sm[0]);
+}
+
+__global__ void recycle_status_kernel(const int* __restrict__ infos, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += infos[i] != 0 ? 1.0 : 0.0;
+    out[0] = s;
+  }
+}
+
+// One Cholesky-QR pass on the rows of T (K x a):  G = T T^H,  G = L L^H,  T <- L^-1 T.
+// Row-major G is the column-major conj(G) = Lc Lc^H with L = conj(Lc); the row-major T is the column-major
+// T^T, and (L^-1 T)^T = T^T (Lc^H)^-1: one right-sided triangular solve with op = conjugate-transpose.
+int cholqr_pass(Solver* s, int dtype, int K, int a, void* T, void* G, void* work, int lwork, int* info_dev, void* stream_) {
+  if (pdmrg_gemm_nt(dtype, K, K, a, 1, T, a, 0, T, a, 0, 1, G, K, 0, 1.0, 0.0, 0, stream_)) return 1;
+  cusolverStatus_t st;
+  if (dtype == PDMRG_C128) st = s->p_cusolverDnZpotrf(s->handle, CUBLAS_FILL_MODE_LOWER, K, (cuDoubleComplex*)G, K, (cuDoubleComplex*)work, lwork, info_dev);
+  else st = s->p_cusolverDnDpotrf(s->handle, CUBLAS_FILL_MODE_LOWER, K, (double*)G, K, (double*)work, lwork, info_dev);
+  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: potrf failed (%d)", (int)st); return 1; }
+  cublasStatus_t bs;
+  if (dtype == PDMRG_C128) {
+    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+    bs = s->p_cublasZtrsm(s->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, a, K, &one,
+                          (const cuDoubleComplex*)G, K, (cuDoubleComplex*)T, a);
+  } else {
+    const double one = 1.0;
+    bs = s->p_cublasDtrsm(s->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, a, K, &one,
+                          (const double*)G, K, (double*)T, a);
+  }
+  if (bs != CUBLAS_STATUS_SUCCESS) { set_error("recycle: trsm failed (%d)", (int)bs); return 1; }
+  count_launch(2);
+  return 0;
+}
+
 }  // namespace
 }  // namespace pdmrg
 
@@ -613,9 +775,9 @@ extern "C" size_t pdmrg_recycle_basis_workspace_bytes(int dtype, int a, int c, i
   return l.total() + 256;
 }
 
-extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, const void* X1, const void* X2, const void* Wt,
-                                   void* Pt, void* Ct, double* S, void* workspace, size_t workspace_bytes, int* info_dev,
-                                   void* stream_) {
+extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b, int method, const void* X1, const void* X2,
+                                   const void* Wt, void* Pt, void* Ct, double* S, void* workspace, size_t workspace_bytes,
+                                   int* info_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Solver* s = get_solver();
   if (!s) return 1;
@@ -634,19 +796,57 @@ extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b,
   void* H = ws + l.tau;
   double* lam = reinterpret_cast<double*>(ws + l.tau + l.H);
   void* Tw = ws + l.tau + l.H + l.lam;
-  void* work = ws + l.tau + l.H + l.lam + l.Tw;
+  void* G = ws + l.tau + l.H + l.lam + l.Tw;
+  void* work = ws + l.tau + l.H + l.lam + l.Tw + l.G;
+  PDMRG_REQUIRE(method == 0 || method == 1, "pdmrg_recycle_basis: method must be 0 (Householder) or 1 (Cholesky-QR2)");
+  PDMRG_CHECK_CUDA(cudaMemsetAsync(info_dev, 0, 4 * sizeof(int), stream));
+  PDMRG_CHECK_CUDA(cudaMemsetAsync(S + K, 0, 2 * sizeof(double), stream));
 
   // T[i, r] = sum_x W[i, x] conj(X1[r, x])     (K x a), written where P will live
   if (pdmrg_gemm_nt(dtype, K, a, c, 1, Wt, c, 0, X1, c, 0, 1, Pt, a, 0, 1.0, 0.0, 0, stream_)) return 1;
-  // Householder QR of the column-major (a x K) view: column i of it is row i of T
   cusolverStatus_t st;
-  if (cplx) st = s->p_cusolverDnZgeqrf(s->handle, a, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
-  else st = s->p_cusolverDnDgeqrf(s->handle, a, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
-  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: geqrf failed (%d)", (int)st); return 1; }
-  if (cplx) st = s->p_cusolverDnZungqr(s->handle, a, K, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
-  else st = s->p_cusolverDnDorgqr(s->handle, a, K, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
-  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: ungqr failed (%d)", (int)st); return 1; }
-  count_launch(2);
+  if (method == 1) {
+    // Cholesky-QR2 on the row-normalised T: triangular like Householder (row i only mixes with rows < i, so the
+    // ordering of the basis survives), all GEMM / potrf / trsm.  Valid while the normalised rows are not
+    // numerically dependent; the defect of the first pass (S[K]) and the potrf infos (S[K+1]) tell the caller.
+    if (s->p_cublasSetStream(s->blas, stream) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return 1; }
+    if (cplx) row_norm_kernel<2><<<K, 256, 0, stream>>>((const double*)Pt, a, S);
+    else row_norm_kernel<1><<<K, 256, 0, stream>>>((const double*)Pt, a, S);
+    PDMRG_CHECK_LAUNCH();
+    if (cplx) row_normalize_kernel<2><<<K, 256, 0, stream>>>((double*)Pt, a, S, K);
+    else row_normalize_kernel<1><<<K, 256, 0, stream>>>((double*)Pt, a, S, K);
+    PDMRG_CHECK_LAUNCH();
+    if (cholqr_pass(s, dtype, K, a, Pt, G, work, l.lwork_elems, info_dev + 1, stream_)) return 1;
+    // second pass; its Gram matrix measures what the first one achieved
+    if (pdmrg_gemm_nt(dtype, K, K, a, 1, Pt, a, 0, Pt, a, 0, 1, G, K, 0, 1.0, 0.0, 0, stream_)) return 1;
+    if (cplx) gram_defect_kernel<2><<<64, 256, 0, stream>>>((const double*)G, K, S + K);
+    else gram_defect_kernel<1><<<64, 256, 0, stream>>>((const double*)G, K, S + K);
+    PDMRG_CHECK_LAUNCH();
+    if (cplx) st = s->p_cusolverDnZpotrf(s->handle, CUBLAS_FILL_MODE_LOWER, K, (cuDoubleComplex*)G, K, (cuDoubleComplex*)work, l.lwork_elems, info_dev + 2);
+    else st = s->p_cusolverDnDpotrf(s->handle, CUBLAS_FILL_MODE_LOWER, K, (double*)G, K, (double*)work, l.lwork_elems, info_dev + 2);
+    if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: potrf failed (%d)", (int)st); return 1; }
+    cublasStatus_t bs;
+    if (cplx) {
+      const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+      bs = s->p_cublasZtrsm(s->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, a, K, &one,
+                            (const cuDoubleComplex*)G, K, (cuDoubleComplex*)Pt, a);
+    } else {
+      const double one = 1.0;
+      bs = s->p_cublasDtrsm(s->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, a, K, &one,
+                            (const double*)G, K, (double*)Pt, a);
+    }
+    if (bs != CUBLAS_STATUS_SUCCESS) { set_error("recycle: trsm failed (%d)", (int)bs); return 1; }
+    count_launch(5);
+  } else {
+    // Householder QR of the column-major (a x K) view: column i of it is row i of T
+    if (cplx) st = s->p_cusolverDnZgeqrf(s->handle, a, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+    else st = s->p_cusolverDnDgeqrf(s->handle, a, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
+    if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: geqrf failed (%d)", (int)st); return 1; }
+    if (cplx) st = s->p_cusolverDnZungqr(s->handle, a, K, K, (cuDoubleComplex*)Pt, a, (cuDoubleComplex*)tau, (cuDoubleComplex*)work, l.lwork_elems, info_dev);
+    else st = s->p_cusolverDnDorgqr(s->handle, a, K, K, (double*)Pt, a, (double*)tau, (double*)work, l.lwork_elems, info_dev);
+    if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: ungqr failed (%d)", (int)st); return 1; }
+    count_launch(2);
+  }
   // C[i, x] = sum_r P[i, r] X2[x, r]            (K x c)
   if (pdmrg_gemm_nt(dtype, K, c, a, 1, Pt, a, 0, X2, a, 0, 0, Ct, c, 0, 1.0, 0.0, 0, stream_)) return 1;
 
@@ -657,7 +857,16 @@ extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b,
     unsigned char* Cw = static_cast<unsigned char*>(Ct) + (size_t)w0 * c * eb;
     unsigned char* Pw = static_cast<unsigned char*>(Pt) + (size_t)w0 * a * eb;
     if (pdmrg_gemm_nt(dtype, w, w, c, 1, Cw, c, 0, Cw, c, 0, 1, H, w, 0, -1.0, 0.0, 0, stream_)) return 1;
-    if (heevd_inplace(s, dtype, w, (double*)H, lam, work, l.lwork_elems, info_dev, stream)) return 1;
+    if (w <= RECYCLE_JACOBI_MAX) {
+      if (cplx) st = s->p_cusolverDnZheevj(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, (cuDoubleComplex*)H, w, lam,
+                                           (cuDoubleComplex*)work, l.lwork_elems, info_dev + 3, s->evj);
+      else st = s->p_cusolverDnDsyevj(s->handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, w, (double*)H, w, lam, (double*)work,
+                                      l.lwork_elems, info_dev + 3, s->evj);
+      if (st != CUSOLVER_STATUS_SUCCESS) { set_error("recycle: heevj failed (%d)", (int)st); return 1; }
+      count_launch();
+    } else {
+      if (heevd_inplace(s, dtype, w, (double*)H, lam, work, l.lwork_elems, info_dev + 3, stream)) return 1;
+    }
     if (pdmrg_permute4(dtype, Cw, Tw, 1, 1, c, w, 0, 0, 1, c, 0, nullptr, 0, stream_)) return 1;       // Tw[x, i] = Cw[i, x]
     if (pdmrg_gemm_nt(dtype, w, c, w, 1, H, w, 0, Tw, w, 0, 0, Cw, c, 0, 1.0, 0.0, 0, stream_)) return 1;
     if (pdmrg_permute4(dtype, Pw, Tw, 1, 1, a, w, 0, 0, 1, a, 0, nullptr, 0, stream_)) return 1;
@@ -666,7 +875,9 @@ extern "C" int pdmrg_recycle_basis(int dtype, int a, int c, int K, int k, int b,
   if (cplx) row_norm_kernel<2><<<K, 256, 0, stream>>>((const double*)Ct, c, S);
   else row_norm_kernel<1><<<K, 256, 0, stream>>>((const double*)Ct, c, S);
   PDMRG_CHECK_LAUNCH();
-  count_launch();
+  recycle_status_kernel<<<1, 32, 0, stream>>>(info_dev, 4, S + K + 1);
+  PDMRG_CHECK_LAUNCH();
+  count_launch(2);
   return 0;
 }
 

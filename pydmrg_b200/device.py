@@ -336,24 +336,37 @@ def left_basis(X, workspace, keep=0):
     return Ut, lam, info
 
 
-def recycle_basis(X1, X2, Wt, k, b, workspace):
+RECYCLE_HOUSEHOLDER = 0
+RECYCLE_CHOLQR2 = 1
+RECYCLE_MAX_DEFECT2 = 1e-2       # ||P1 P1^H - I||_F^2 tolerated after the first Cholesky pass (the second squares it)
+
+
+def recycle_basis(X1, X2, Wt, k, b, workspace, method=None):
     """One warm-started subspace step (csrc/solver.cu pdmrg_recycle_basis): X1 (a,c), X2 = X1^T (c,a),
-    Wt (K,c) previous basis rows (k kept + K-k spare).  Returns Pt (K,a), Ct (K,c), S (K,), info."""
+    Wt (K,c) previous basis rows (k kept + K-k spare).  Returns Pt (K,a), Ct (K,c), S (K,) on the HOST,
+    ok, method_used.  ``method`` None: Cholesky-QR2 first, Householder QR when its first pass was not
+    well conditioned (or cuSOLVER reported a failure)."""
     code = dtype_code(X1)
     a, c = X1.shape
     K = Wt.shape[0]
     assert X2.shape == (c, a) and Wt.shape[1] == c and X1.is_contiguous() and X2.is_contiguous() and Wt.is_contiguous()
     Pt = torch.empty((K, a), dtype=X1.dtype, device=X1.device)
     Ct = torch.empty((K, c), dtype=X1.dtype, device=X1.device)
-    S = torch.empty(K, dtype=torch.float64, device=X1.device)
-    info = torch.zeros(1, dtype=torch.int32, device=X1.device)
+    S = torch.empty(K + 2, dtype=torch.float64, device=X1.device)
+    info = torch.zeros(4, dtype=torch.int32, device=X1.device)
     nb = int(lib.pdmrg_recycle_basis_workspace_bytes(code, a, c, K, int(k), int(b)))
     if nb == 0:
         check(1, "pdmrg_recycle_basis_workspace_bytes")
     ws = workspace.get(nb)
-    check(lib.pdmrg_recycle_basis(code, a, c, K, int(k), int(b), _ptr(X1), _ptr(X2), _ptr(Wt), _ptr(Pt), _ptr(Ct), _ptr(S),
-                                  _ptr(ws), ws.numel(), _ptr(info), _stream()), "pdmrg_recycle_basis")
-    return Pt, Ct, S, info
+    Sh = None
+    for meth in ([RECYCLE_CHOLQR2, RECYCLE_HOUSEHOLDER] if method is None else [method]):
+        check(lib.pdmrg_recycle_basis(code, a, c, K, int(k), int(b), int(meth), _ptr(X1), _ptr(X2), _ptr(Wt), _ptr(Pt),
+                                      _ptr(Ct), _ptr(S), _ptr(ws), ws.numel(), _ptr(info), _stream()), "pdmrg_recycle_basis")
+        Sh = S.cpu().numpy()                                    # sync
+        ok = bool(np.all(np.isfinite(Sh))) and Sh[K + 1] == 0 and Sh[K] < RECYCLE_MAX_DEFECT2
+        if ok:
+            return Pt, Ct, Sh[:K], True, meth
+    return Pt, Ct, Sh[:K], False, meth
 
 
 def heevd(a, workspace):

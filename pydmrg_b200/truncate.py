@@ -112,7 +112,7 @@ def eig_truncate(psi, shape, mbd, ctx, direction, spare=0, extras=None):
     return A, B, Sn, EE, EEs
 
 
-def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext):
+def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext, method=None):
     """Projective truncation warm-started from the bond's previous bases (csrc/solver.cu
     pdmrg_recycle_basis; same outputs as eig_truncate plus the new spare rows, or None when it cannot be
     used).  ``warm`` is the site tensor holding the previous basis of the side that is NOT being left
@@ -139,9 +139,8 @@ def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext):
         D.permute4(warm, Wt, (k, Dl, d1), (1, k, Dl * k))           # Wt[i,(l,n)] = A0[n,l,i]
     Wt[k:].copy_(ext)
     b = min(k, max(2, k // RECYCLE_FRACTION))
-    Pt, Ct, S, info = D.recycle_basis(X1, X2, Wt, k, b, ctx.svd_ws)
-    Sh = S.cpu().numpy()                                            # sync
-    if int(info.item()) != 0 or not np.all(np.isfinite(Sh)):
+    Pt, Ct, Sh, ok, used = D.recycle_basis(X1, X2, Wt, k, b, ctx.svd_ws, method=method)
+    if not ok:
         return None
     EE, EEs, Sn = calc_entanglement(Sh[:k])
     A = ctx.empty(d1, Dl, k)
@@ -154,7 +153,7 @@ def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext):
         D.permute4(Ct, A, (d1, Dl, k), (1, d1, c))                  # A[n,l,i] = C[i,(l,n)]
     new_ext = ctx.empty(p, a)
     D.permute4(Pt[k:], new_ext, (p, a), (a, 1), conj=True)
-    return A, B, Sn, EE, EEs, new_ext
+    return A, B, Sn, EE, EEs, new_ext, used
 
 
 def full_rank_split(psi, shape, ctx, direction):
@@ -184,7 +183,10 @@ def full_rank_split(psi, shape, ctx, direction):
         mT = ctx.empty(cols, rows)
         D.permute4(m, mT, (cols, rows), (1, cols))
         a, c, X1, X2 = (rows, cols, m, mT) if right else (cols, rows, mT, m)
-        Pt, Ct, S, info = D.recycle_basis(X1, X2, eye(c), k, 0, ctx.svd_ws)
+        Pt, Ct, Sq, ok, _ = D.recycle_basis(X1, X2, eye(c), k, 0, ctx.svd_ws, method=D.RECYCLE_HOUSEHOLDER)
+        if not ok:
+            return None
+        S = torch.from_numpy(Sq)
         if right:
             D.permute4(Pt, A, (d1, Dl, k), (1, d1, a), conj=True)
             D.permute4(Ct, B, (d2, k, Dr), (Dr, c, 1))
@@ -238,9 +240,14 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
         want = (d2, k, Dr) if right else (d1, Dl, k)
         if is_dev(top) and tuple(top.shape) == want and top.dtype == ctx.tdtype and ext.dtype == ctx.tdtype \
                 and tuple(ext.shape) == (p, cols if right else rows):
-            r = recycled_truncate(psi, shape, mbd, ctx, direction, top.contiguous(), ext)
+            # a bond where the Cholesky-QR2 variant had to be redone with Householder QR keeps using the latter
+            r = recycled_truncate(psi, shape, mbd, ctx, direction, top.contiguous(), ext, method=recycle.get(("qr", site)))
             if r is not None:
                 recycle[(site, other)] = r[5]
+                if r[6] == D.RECYCLE_HOUSEHOLDER:
+                    recycle[("qr", site)] = D.RECYCLE_HOUSEHOLDER
+                    if stats is not None:
+                        stats["n_householder"] = stats.get("n_householder", 0) + 1
                 if stats is not None:
                     stats["n_recycled"] = stats.get("n_recycled", 0) + 1
                 return r[:5]

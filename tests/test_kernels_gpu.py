@@ -391,3 +391,65 @@ def test_sharded_paths_two_gpus():
                         os.path.join(root, "tests", "mgpu_sharded_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK" in r.stdout
+
+
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+@pytest.mark.parametrize("method", [0, 1])
+def test_recycle_basis_methods(dtype, method):
+    """pdmrg_recycle_basis, Householder (0) and Cholesky-QR2 (1): P has orthonormal rows, C = P X2^T, the rows
+    keep the nested ordering (row i only mixes with rows <= i outside the window), the window rows of C are
+    mutually orthogonal and sorted, and both methods span the same kept subspace."""
+    import torch
+    from pydmrg_b200 import core, device as D
+    ctx = core.Context(dtype)
+    rng = np.random.default_rng(11)
+    a, c, k, p, b = 192, 160, 64, 8, 8
+    K = k + p
+    cplx = dtype == "c128"
+    rnd = (lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)) if cplx else (lambda *s: rng.standard_normal(s))
+    U, _ = np.linalg.qr(rnd(a, a)); V, _ = np.linalg.qr(rnd(c, c))
+    q = min(a, c)
+    s = np.exp(-np.arange(q) * 0.15)
+    X1 = (U[:, :q] * s) @ V[:, :q].conj().T                       # (a, c)
+    W = V[:, :K].conj().T + 1e-5 * rnd(K, c)                       # rows ~ conj(right vectors)^T, slightly off
+    Pt, Ct, Sh, ok, used = D.recycle_basis(ctx.dev(X1), ctx.dev(np.ascontiguousarray(X1.T)), ctx.dev(np.ascontiguousarray(W)), k, b,
+                                           ctx.svd_ws, method=method)
+    assert ok and used == method
+    P, C = ctx.host(Pt), ctx.host(Ct)
+    assert np.max(np.abs(P @ P.conj().T - np.eye(K))) < 1e-12
+    assert np.max(np.abs(C - P @ X1)) < 1e-12 * s[0] * a          # C[i,x] = sum_r P[i,r] X1[r,x]
+    assert np.max(np.abs(Sh - np.linalg.norm(C, axis=1))) < 1e-12
+    # rows of P are conj(left vectors): P[i] ~ conj(u_i) up to a phase for well separated weights
+    ov = np.abs(P[: k - b] @ U[:, : k - b])                        # sum_r conj(u_i)[r] u_j[r]
+    assert np.max(np.abs(np.diag(ov) - 1.0)) < 1e-6
+    # window: C rows orthogonal, norms descending and equal to the singular values there
+    w0 = k - b
+    Cw = C[w0:]
+    Gw = Cw @ Cw.conj().T
+    assert np.max(np.abs(Gw - np.diag(np.diag(Gw)))) < 1e-12 * s[w0] ** 2 * 10
+    assert np.all(np.diff(Sh[w0:]) <= 1e-15)
+    assert np.max(np.abs(Sh[:K] - s[:K])) < 1e-8 * s[0]
+
+
+def test_recycle_basis_rank_deficient_cholqr():
+    """Rank-deficient wave-function (numerical rank 12 << K): the noise rows of T are replaced by pseudo-random
+    vectors, so the Cholesky-QR2 route still delivers an orthonormal basis whose leading rows span the range."""
+    import torch
+    from pydmrg_b200 import core, device as D
+    ctx = core.Context("c128")
+    rng = np.random.default_rng(4)
+    a, c, k, p, r0 = 256, 256, 128, 16, 12
+    K = k + p
+    rnd = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    U, _ = np.linalg.qr(rnd(a, a)); V, _ = np.linalg.qr(rnd(c, c))
+    s = np.zeros(a); s[:r0] = np.exp(-np.arange(r0) * 0.8)
+    X1 = (U * s) @ V.conj().T
+    W = V[:, :K].conj().T.copy()
+    Pt, Ct, Sh, ok, used = D.recycle_basis(ctx.dev(X1), ctx.dev(np.ascontiguousarray(X1.T)), ctx.dev(W), k, 16, ctx.svd_ws,
+                                           method=D.RECYCLE_CHOLQR2)
+    assert ok and used == D.RECYCLE_CHOLQR2
+    P, C = ctx.host(Pt), ctx.host(Ct)
+    assert np.max(np.abs(P @ P.conj().T - np.eye(K))) < 1e-12
+    assert np.max(np.abs(Sh[:r0] - s[:r0])) < 1e-12 and np.max(Sh[r0:]) < 1e-13
+    # projection on the kept rows loses nothing
+    assert abs(np.linalg.norm(C[:k]) - np.linalg.norm(X1)) < 1e-13

@@ -423,7 +423,7 @@ def test_recycled_truncate_matches_exact(P, direction, dtype):
     ext = c.dev(np.ascontiguousarray(Wfull[k:]))
     out = P.truncate.recycled_truncate(c.dev(psi), (d1, d2, Dl, Dr), k, c, direction, c.dev(warm), ext)
     assert out is not None
-    A, B, Sn, EE, EEs, new_ext = out
+    A, B, Sn, EE, EEs, new_ext, _ = out
     A, B = c.host(A), c.host(B)
     Sx = s[:k] / np.linalg.norm(s[:k])
     assert np.max(np.abs(Sn - Sx)) < 1e-8          # one step from a 1e-6 perturbation (error is second order)
