@@ -345,6 +345,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         line["sharded"]["ket_split_nccl"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
                                              "how": "left ket index split N ways (balanced), 1 NCCL all-reduce of y"}
+        # the same split with the exchange fused into the kernels (long-K stage C, scatter epilogue, peer stores)
+        fk = parallel.FusedShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist, mode="ket")
+        for _ in range(3):
+            fk.apply(xs, ys)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            fk.apply(xs, ys)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["sharded"]["ket_split_fused"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
+                                              "how": "ket split; stage C = one long-K GEMM whose scatter epilogue reduce-scatters the "
+                                                     "partial y over NVLink, then a flag-guarded reduce + all-gather kernel (no NCCL)"}
+        fk.close()
 
     # ---- extras on rank 0 at N=1: bond step, sweep estimate, CPU baseline ----------------------
     if world == 1 and not args.no_extras:

@@ -130,13 +130,23 @@ int pdmrg_heff_apply_fused(pdmrg_heff_plan* plan, pdmrg_comm* comm, const void* 
                            const void* const* R_host_ptrs, const void* x, void* y, double sign,
                            const unsigned int* jmask_all_ranks, void* workspace, size_t workspace_bytes,
                            void* stream);
-/* the GEMM with the scatter epilogue on its own: rows [q*rows_per_owner, ...) of C go to Cpeer_host[q] */
+/* the GEMM with the scatter epilogue on its own: rows [q*rows_per_owner, ...) of C go to Cpeer_host[q].
+ * accumulate_b2 != 0: the nb2 second-level batch entries are summed into ONE output per b1 (their
+ * k-ranges are concatenated inside the kernel's k-loop; strideC2 is ignored). */
 int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
                           const void* A, long long lda, long long strideA1, long long strideA2,
                           const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
                           const void* const* Cpeer_host, int n_owner, int rows_per_owner,
                           long long ldc, long long strideC1, long long strideC2,
-                          double alpha_re, double alpha_im, void* stream);
+                          double alpha_re, double alpha_im, int accumulate_b2, void* stream);
+/* Ket-split mat-vec with the exchange fused into the kernels: `plan` from pdmrg_heff_plan_create_ketsplit
+ * (this rank's ket range), stage C runs as ONE long-K GEMM (MPO bond folded into the k-loop) whose scatter
+ * epilogue stores every tile of this rank's PARTIAL y straight into the owner rank's buffer
+ * Z[src][pout][il][r]; the flag-guarded reduce + all-gather kernel then sums the `world` partials and
+ * pushes the rows to every rank.  Z needs world * P * chunk * Dr elements (pdmrg_comm_z_bytes suffices). */
+int pdmrg_heff_apply_fused_ket(pdmrg_heff_plan* plan, pdmrg_comm* comm, const void* const* L_host_ptrs,
+                               const void* const* R_host_ptrs, const void* x, void* y, double sign,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Ket-split shard: this rank contracts only the ket indices k in [k0, k0+klen) of the LEFT bond
  * (x[pin, k, s], L[i, j, k]); x and y keep their full (P, Dl, Dr) shape, y holds the PARTIAL sum.

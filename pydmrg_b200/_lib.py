@@ -55,7 +55,8 @@ def _load():
         "pdmrg_comm_y_bytes": (sz, [vp]),
         "pdmrg_heff_needed_j": (i, [vp, i, POINTER(ctypes.c_uint)]),
         "pdmrg_heff_apply_fused": (i, [vp, vp, POINTER(vp), POINTER(vp), vp, vp, d, POINTER(ctypes.c_uint), vp, sz, vp]),
-        "pdmrg_gemm_nt_scatter": (i, [i, i, i, i, i, i, POINTER(i), vp, ll, ll, ll, vp, ll, ll, ll, i, POINTER(vp), i, i, ll, ll, ll, d, d, vp]),
+        "pdmrg_gemm_nt_scatter": (i, [i, i, i, i, i, i, POINTER(i), vp, ll, ll, ll, vp, ll, ll, ll, i, POINTER(vp), i, i, ll, ll, ll, d, d, i, vp]),
+        "pdmrg_heff_apply_fused_ket": (i, [vp, vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp]),
         "pdmrg_heff_flops_dense": (d, [vp]),
         "pdmrg_heff_flops_sparse": (d, [vp]),
         "pdmrg_heff_flops_gemm": (d, [vp]),

@@ -52,6 +52,9 @@ struct GemmParams {
   // GEMM epilogue, tile by tile, as plain st.global over NVLink
   double* Cpeer[8];
   int rows_per_owner;
+  // accum2: the nb2 entries of the second batch level are SUMMED into one output tile (the k-loop runs over
+  // all of them) instead of producing nb2 separate outputs -- a long-K product whose K is not contiguous
+  int accum2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -115,7 +118,9 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
 
   constexpr int BM = 16 * MI;                       // 128 or 64 rows per CTA tile
-  const int total_tiles = p.tiles_m * p.tiles_n * p.nb1 * p.nb2;
+  const int nb2_out = p.accum2 ? 1 : p.nb2;            // outputs along the second batch level
+  const int nb2_k = p.accum2 ? p.nb2 : 1;              // second-level entries folded into the k-loop
+  const int total_tiles = p.tiles_m * p.tiles_n * p.nb1 * nb2_out;
   constexpr int B_ROWS = CPLX ? BNR / 2 : BNR;
   constexpr uint32_t TX_BYTES = BM * BK * 8 + B_ROWS * BK * 8;
 
@@ -130,17 +135,20 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tn = rest % p.tiles_n;
         const int b = rest / p.tiles_n;
         const int rowA = tm * BM, rowB = tn * B_ROWS;
-        const int b1 = b / p.nb2, b2 = p.idx2[b % p.nb2];
-        const int a1 = p.bcastA1 ? 0 : b1, a2 = p.bcastA2 ? 0 : b2;
-        const int c1 = p.bcastB1 ? 0 : b1, c2 = p.bcastB2 ? 0 : b2;
-        for (int kit = 0; kit < p.kiters; ++kit) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t full = full0 + 8 * stage;
-          mbar_expect_tx(full, TX_BYTES);
-          const uint32_t sA = smem_base + stage * STAGE_BYTES;
-          tma_load_4d(sA, &tmA, kit * BK, rowA, a2, a1, full);
-          tma_load_4d(sA + A_BYTES, &tmB, kit * BK, rowB, c2, c1, full);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const int b1 = b / nb2_out;
+        const int a1 = p.bcastA1 ? 0 : b1, c1 = p.bcastB1 ? 0 : b1;
+        for (int q = 0; q < nb2_k; ++q) {
+          const int b2 = p.idx2[p.accum2 ? q : b % p.nb2];
+          const int a2 = p.bcastA2 ? 0 : b2, c2 = p.bcastB2 ? 0 : b2;
+          for (int kit = 0; kit < p.kiters; ++kit) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t full = full0 + 8 * stage;
+            mbar_expect_tx(full, TX_BYTES);
+            const uint32_t sA = smem_base + stage * STAGE_BYTES;
+            tma_load_4d(sA, &tmA, kit * BK, rowA, a2, a1, full);
+            tma_load_4d(sA + A_BYTES, &tmB, kit * BK, rowB, c2, c1, full);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -180,7 +188,8 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    for (int kit = 0; kit < p.kiters; ++kit) {
+    const int ktot = p.kiters * nb2_k;
+    for (int kit = 0; kit < ktot; ++kit) {
       mbar_wait(full0 + 8 * stage, phase);
       const unsigned char* sA = smem + stage * STAGE_BYTES;
       const unsigned char* sB = sA + A_BYTES;
@@ -216,7 +225,8 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     // ------------------------------ epilogue ----------------------------------------
-    const long long boff = (CPLX ? 2 : 1) * ((long long)(b / p.nb2) * p.strideC1 + (long long)p.idx2[b % p.nb2] * p.strideC2);
+    const long long boff = (CPLX ? 2 : 1) * ((long long)(b / nb2_out) * p.strideC1 +
+                                             (p.accum2 ? 0ll : (long long)p.idx2[b % p.nb2] * p.strideC2));
     double* Cb = p.C + boff;
     const int row0 = tm * BM + wm * (8 * MI) + permg;
     if (CPLX) {
@@ -410,7 +420,7 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
                         const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
                         void* C, long long ldc, long long strideC1, long long strideC2,
                         double alpha_re, double alpha_im, int beta, void* stream_,
-                        const void* const* Cpeer, int n_owner, int rows_per_owner);
+                        const void* const* Cpeer, int n_owner, int rows_per_owner, int accum2);
 
 extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
                                       const void* A, long long lda, long long strideA1, long long strideA2,
@@ -418,7 +428,7 @@ extern "C" int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, i
                                       void* C, long long ldc, long long strideC1, long long strideC2,
                                       double alpha_re, double alpha_im, int beta, void* stream_) {
   return gemm_nt_impl(dtype, M, N, K, nb1, nb2, idx2_host, A, lda, strideA1, strideA2, B, ldb, strideB1, strideB2, conjB, C, ldc,
-                      strideC1, strideC2, alpha_re, alpha_im, beta, stream_, nullptr, 0, 0);
+                      strideC1, strideC2, alpha_re, alpha_im, beta, stream_, nullptr, 0, 0, 0);
 }
 
 extern "C" int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
@@ -426,12 +436,12 @@ extern "C" int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, in
                                      const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
                                      const void* const* Cpeer_host, int n_owner, int rows_per_owner,
                                      long long ldc, long long strideC1, long long strideC2,
-                                     double alpha_re, double alpha_im, void* stream_) {
+                                     double alpha_re, double alpha_im, int accumulate_b2, void* stream_) {
   PDMRG_REQUIRE(n_owner >= 1 && n_owner <= 8 && rows_per_owner > 0, "pdmrg_gemm_nt_scatter: bad owner layout");
   PDMRG_REQUIRE((long long)n_owner * rows_per_owner >= M, "pdmrg_gemm_nt_scatter: owners do not cover the rows");
   return gemm_nt_impl(dtype, M, N, K, nb1, nb2, idx2_host, A, lda, strideA1, strideA2, B, ldb, strideB1, strideB2, conjB,
                       const_cast<void*>(Cpeer_host[0]), ldc, strideC1, strideC2, alpha_re, alpha_im, 0, stream_, Cpeer_host, n_owner,
-                      rows_per_owner);
+                      rows_per_owner, accumulate_b2 ? 1 : 0);
 }
 
 static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
@@ -439,7 +449,7 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
                         const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
                         void* C, long long ldc, long long strideC1, long long strideC2,
                         double alpha_re, double alpha_im, int beta, void* stream_,
-                        const void* const* Cpeer, int n_owner, int rows_per_owner) {
+                        const void* const* Cpeer, int n_owner, int rows_per_owner, int accum2) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_gemm_nt: bad dtype");
   PDMRG_REQUIRE(beta == 0 || beta == 1, "pdmrg_gemm_nt: beta must be 0 or 1");
@@ -458,12 +468,12 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
     PDMRG_REQUIRE(p.idx2[i] >= 0, "pdmrg_gemm_nt: negative batch index");
     if (p.idx2[i] > max2) max2 = p.idx2[i];
   }
-  const long long nbatch = (long long)nb1 * nb2;
+  const long long nbatch = (long long)nb1 * (accum2 ? 1 : nb2);       // output batches
 
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   auto even = [&](long long v) { return (v * E) % 2 == 0; };
   const bool strides_ok = even(lda) && even(ldb) && even(strideA1) && even(strideA2) && even(strideB1) && even(strideB2);
-  const double work = (double)M * N * (double)(K > 0 ? K : 1) * (double)nbatch * (cplx ? 4 : 1);
+  const double work = (double)M * N * (double)(K > 0 ? K : 1) * (double)nb1 * nb2 * (cplx ? 4 : 1);
   const bool use_tma = !g_force_generic.load() && K > 0 && aligned16(A) && aligned16(B) && strides_ok &&
                        (!cplx || aligned16(C)) && work >= 64.0 * 64.0 * 64.0;
 
@@ -477,6 +487,7 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
   p.bcastB1 = (strideB1 == 0 || nb1 == 1); p.bcastB2 = (strideB2 == 0 || max2 == 0);
   for (int i = 0; i < 8; ++i) p.Cpeer[i] = (Cpeer && i < n_owner) ? static_cast<double*>(const_cast<void*>(Cpeer[i])) : nullptr;
   p.rows_per_owner = rows_per_owner > 0 ? rows_per_owner : 1;
+  p.accum2 = accum2;
   const bool scatter = Cpeer != nullptr;
   if (scatter) PDMRG_REQUIRE(beta == 0, "pdmrg_gemm_nt_scatter: beta must be 0");
 
@@ -530,7 +541,7 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
     return 0;
   }
 
-  PDMRG_REQUIRE(!scatter, "pdmrg_gemm_nt_scatter: operands must be TMA-compatible (16-byte aligned, even strides)");
+  PDMRG_REQUIRE(!scatter && !accum2, "pdmrg_gemm_nt_scatter: operands must be TMA-compatible (16-byte aligned, even strides)");
   dim3 grid((N + 31) / 32, (M + 31) / 32, (unsigned)nbatch);
   PDMRG_REQUIRE(grid.y <= 65535 && nbatch <= 65535, "pdmrg_gemm_nt: generic path extent too large");
   p.kiters = 0; p.tiles_m = p.tiles_n = 0;

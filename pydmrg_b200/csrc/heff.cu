@@ -17,13 +17,6 @@
 
 using namespace pdmrg;
 
-extern "C" int pdmrg_gemm_nt_scatter(int dtype, int M, int N, int K, int nb1, int nb2, const int* idx2_host,
-                                     const void* A, long long lda, long long strideA1, long long strideA2,
-                                     const void* B, long long ldb, long long strideB1, long long strideB2, int conjB,
-                                     const void* const* Cpeer_host, int n_owner, int rows_per_owner,
-                                     long long ldc, long long strideC1, long long strideC2,
-                                     double alpha_re, double alpha_im, void* stream_);
-
 struct pdmrg_heff_plan {
   int dtype, P, Dl, Dr, n_mpo;
   std::vector<int> wL, wR;
@@ -321,11 +314,61 @@ extern "C" int pdmrg_heff_apply_fused(pdmrg_heff_plan* pl, pdmrg_comm* comm, con
     for (int q = 0; q < world; ++q) Cpeer[q] = comm_zpeer(comm, q) + (size_t)E * rank * P * wl * chunk * Dr;
     if (pdmrg_gemm_nt_scatter(pl->dtype, Dl, Dr, Dl, P, (int)jlist.size(), jlist.data(), L, (long long)wl * Dl, 0, Dl,
                               U, (long long)wl * Dl, (long long)Dr * wl * Dl, Dl, 0, Cpeer, world, chunk, Dr,
-                              (long long)wl * chunk * Dr, (long long)chunk * Dr, 1.0, 0.0, stream))
+                              (long long)wl * chunk * Dr, (long long)chunk * Dr, 1.0, 0.0, 0, stream))
       return 1;
   }
   if (comm_signal(comm, 0, stream)) return 1;
   if (comm_reduce_gather(comm, jmask_all_ranks, P, wl, chunk, Dl, Dr, E, sign, stream)) return 1;
+  if (comm_signal(comm, 1, stream)) return 1;
+  if (comm_wait_copy(comm, y, (long long)P * Dl * Dr * E, stream)) return 1;
+  return 0;
+}
+
+extern "C" int pdmrg_heff_apply_fused_ket(pdmrg_heff_plan* pl, pdmrg_comm* comm, const void* const* Ls, const void* const* Rs,
+                                          const void* x, void* y, double sign, void* workspace, size_t workspace_bytes,
+                                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(pl && comm, "pdmrg_heff_apply_fused_ket: null plan / communicator");
+  PDMRG_REQUIRE(pl->n_mpo == 1, "pdmrg_heff_apply_fused_ket: one MPO term per plan");
+  PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply_fused_ket: workspace too small");
+  const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
+  const int P = pl->P, Dl = pl->Dl, Dr = pl->Dr, wl = pl->wL[0], wr = pl->wR[0];
+  const int kl = pl->kl, k0 = pl->k0;
+  const int world = comm_world(comm), rank = comm_rank(comm);
+  const int chunk = (Dl + world - 1) / world;
+  const size_t t_elems = (size_t)Dr * (wr > wl ? wr : wl) * P * Dl;
+  double* T = static_cast<double*>(workspace);
+  double* U = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align_up(t_elems * 8 * E, 256));
+  std::vector<int> olist, jlist;
+  for (int o = 0; o < wr; ++o) if (pl->need_o[0][o]) olist.push_back(o);
+  for (int j = 0; j < wl; ++j) if (pl->need_j[0][j]) jlist.push_back(j);
+  PDMRG_REQUIRE(olist.size() <= 32 && jlist.size() <= 32, "pdmrg_heff_apply_fused_ket: MPO bond above 32");
+  PDMRG_REQUIRE(kl > 0 && !olist.empty() && !jlist.empty(), "pdmrg_heff_apply_fused_ket: every rank needs a non-empty ket range");
+  comm_next_epoch(comm);
+  {
+    const double* R = static_cast<const double*>(Rs[0]);
+    const double* L = static_cast<const double*>(Ls[0]);
+    if (pdmrg_gemm_nt_batched2(pl->dtype, Dr, kl, Dr, P, (int)olist.size(), olist.data(), R, (long long)wr * Dr, 0, Dr,
+                               static_cast<const double*>(x) + (size_t)E * k0 * Dr, Dr, (long long)Dl * Dr, 0, 0,
+                               T, (long long)wr * P * kl, kl, (long long)P * kl, 1.0, 0.0, 0, stream))
+      return 1;
+    if (launch_mix(pl->dtype, pl->mix[0], T, U, Dr, kl, (long long)wr * P * kl, 1, (long long)wl * kl, 1, stream)) return 1;
+    // stage C as ONE long-K product: y_partial[pout][i, r] = sum_j sum_{k in range} L[i, j, k] U[pout][r, j, k]
+    // (the |j| slabs are folded into the k-loop), tiles scattered to Z_q[src = rank][pout][il][r]
+    const void* Cpeer[8];
+    for (int q = 0; q < world; ++q) Cpeer[q] = comm_zpeer(comm, q) + (size_t)E * rank * P * chunk * Dr;
+    if (pdmrg_gemm_nt_scatter(pl->dtype, Dl, Dr, kl, P, (int)jlist.size(), jlist.data(),
+                              L + (size_t)E * k0, (long long)wl * Dl, 0, Dl,
+                              U, (long long)wl * kl, (long long)Dr * wl * kl, kl, 0, Cpeer, world, chunk, Dr,
+                              (long long)chunk * Dr, 0, 1.0, 0.0, 1, stream))
+      return 1;
+  }
+  // every rank contributes exactly one slab per pout (ranks with an empty range contribute none): the masks
+  // are the same on all ranks because the ket ranges are (empty only for world > Dl, which create() rejects)
+  unsigned int masks[8];
+  for (int q = 0; q < 8; ++q) masks[q] = q < world ? 1u : 0u;
+  if (comm_signal(comm, 0, stream)) return 1;
+  if (comm_reduce_gather(comm, masks, P, 1, chunk, Dl, Dr, E, sign, stream)) return 1;
   if (comm_signal(comm, 1, stream)) return 1;
   if (comm_wait_copy(comm, y, (long long)P * Dl * Dr * E, stream)) return 1;
   return 0;

@@ -214,17 +214,23 @@ class FusedShardedHeff:
     64-byte IPC handles and the slab masks between the ranks.  world == 1 runs the same kernels on
     the local buffers."""
 
-    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist=None):
+    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist=None, mode="bond"):
         import ctypes
         import torch
         from . import device as D
         from ._lib import check, lib
         assert len(ops) == 1, "one MPO term per fused plan"
-        self.rank, self.world = rank, world
+        assert mode in ("bond", "ket")
+        self.rank, self.world, self.mode = rank, world, mode
         L, Wc, R = ops[0]
-        pat = block_pattern(Wc, L.shape[1], R.shape[1], P)
-        self.partition = [partition_blocks(pat, world)]
-        self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, block_masks=[self.partition[0][rank]])
+        if mode == "bond":
+            pat = block_pattern(Wc, L.shape[1], R.shape[1], P)
+            self.partition = [partition_blocks(pat, world)]
+            self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, block_masks=[self.partition[0][rank]])
+        else:
+            # ket split: stage C runs as one long-K GEMM whose scatter epilogue reduce-scatters the partial y
+            self.partition = None
+            self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, k_range=ket_chunks(Dl, world)[rank])
         self.n = self.plan.n
         self._lib, self._check, self._ct = lib, check, ctypes
         sizes = [int(lib.pdmrg_comm_z_bytes(self.plan._plan, world)), int(lib.pdmrg_comm_y_bytes(self.plan._plan)),
@@ -268,6 +274,10 @@ class FusedShardedHeff:
         from . import device as D
         pl = self.plan
         ws = pl.workspace.get(pl.ws_bytes)
+        if self.mode == "ket":
+            self._check(self._lib.pdmrg_heff_apply_fused_ket(pl._plan, self._comm, pl._Lp, pl._Rp, D._ptr(x), D._ptr(y), float(sign),
+                                                             D._ptr(ws), ws.numel(), D._stream()), "pdmrg_heff_apply_fused_ket")
+            return y
         self._check(self._lib.pdmrg_heff_apply_fused(pl._plan, self._comm, pl._Lp, pl._Rp, D._ptr(x), D._ptr(y), float(sign),
                                                      self._jmask, D._ptr(ws), ws.numel(), D._stream()), "pdmrg_heff_apply_fused")
         return y

@@ -31,7 +31,15 @@ def main():
     y_f = torch.empty_like(x)
     for _ in range(4):
         fused.apply(x, y_f)
+    fket = parallel.FusedShardedHeff(D.C128, 4, chi, chi, [(L, Wc, R)], ctx.ws, rank, world, dist, mode="ket")
+    y_fk = torch.empty_like(x)
+    for _ in range(4):
+        fket.apply(x, y_fk)
     torch.cuda.synchronize()
+    e_fk = ((y_fk - y_ref).norm() / y_ref.norm()).item()
+    chk2 = torch.view_as_real(y_fk).clone()
+    ref2 = chk2.clone(); dist.broadcast(ref2, 0)
+    same_k = bool(torch.equal(chk2, ref2))
     e_n = ((y_n - y_ref).norm() / y_ref.norm()).item()
     e_f = ((y_f - y_ref).norm() / y_ref.norm()).item()
     e_k = ((y_k - y_ref).norm() / y_ref.norm()).item()
@@ -54,21 +62,25 @@ def main():
     t_nccl = timeit(lambda: nccl.apply(x, y_n))
     t_fused = timeit(lambda: fused.apply(x, y_f))
     t_ket = timeit(lambda: ket.apply(x, y_k))
+    t_fket = timeit(lambda: fket.apply(x, y_fk))
     # stress: back-to-back applies with no host synchronisation in between (the exchange flags and the
     # GEMM's shared-memory ring are the only ordering); every batch must reproduce the reference
     worst = 0.0
     for _ in range(int(os.environ.get("PDMRG_CHECK_BATCHES", "12"))):
         for _ in range(4):
             fused.apply(x, y_f)
+        for _ in range(4):
+            fket.apply(x, y_fk)
         torch.cuda.synchronize()
-        worst = max(worst, ((y_f - y_ref).norm() / y_ref.norm()).item())
-    ok = e_n < 1e-13 and e_f < 1e-13 and e_k < 1e-13 and same and worst < 1e-13
+        worst = max(worst, ((y_f - y_ref).norm() / y_ref.norm()).item(), ((y_fk - y_ref).norm() / y_ref.norm()).item())
+    ok = e_n < 1e-13 and e_f < 1e-13 and e_k < 1e-13 and e_fk < 1e-13 and same and same_k and worst < 1e-13
     if rank == 0:
-        print("chi %d world %d: err bond/nccl %.2e bond/fused %.2e ket/nccl %.2e bit-identical %s stress %.2e | ms unsharded %.3f "
-              "bond+nccl %.3f bond+fused %.3f ket+nccl %.3f"
-              % (chi, world, e_n, e_f, e_k, same, worst, t_full, t_nccl, t_fused, t_ket), flush=True)
+        print("chi %d world %d: err bond/nccl %.2e bond/fused %.2e ket/nccl %.2e ket/fused %.2e bit-identical %s %s stress %.2e | "
+              "ms unsharded %.3f bond+nccl %.3f bond+fused %.3f ket+nccl %.3f ket+fused %.3f"
+              % (chi, world, e_n, e_f, e_k, e_fk, same, same_k, worst, t_full, t_nccl, t_fused, t_ket, t_fket), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     fused.close()
+    fket.close()
     dist.barrier()
     if rank == 0 and flag.item() == 1:
         print("SHARDED_OK", flush=True)
