@@ -357,9 +357,11 @@ def test_heevd(D, ws, real):
     assert rel(rho @ vecs.T, vecs.T * w) < 1e-11
 
 
-def test_fused_sharded_path_world1(D, ws):
+@pytest.mark.parametrize("mode", ["bond", "ket"])
+def test_fused_sharded_path_world1(D, ws, mode):
     """Peer-memory path (scatter-epilogue GEMM, flags, reduce + all-gather kernel) with a single rank:
-    must reproduce the plain mat-vec."""
+    must reproduce the plain mat-vec.  mode='ket' runs stage C as one long-K GEMM (MPO-bond slabs folded
+    into the k-loop, pdmrg_gemm_nt_scatter(accumulate_b2=1))."""
     from pydmrg_b200 import mpo as M, parallel
     chi = 192
     W1, W2 = M.asep_mpo(6, (0.35, 0.0, 1.0, 0.0, 2 / 3, 0.0, -0.5))[0][2:4]
@@ -370,7 +372,7 @@ def test_fused_sharded_path_world1(D, ws):
     x = torch.randn(4 * chi * (chi - 16), dtype=torch.complex128, device="cuda")
     plan = D.HeffPlan(D.C128, 4, chi, chi - 16, [(L, Wc, R)], ws)
     y0 = torch.empty_like(x); plan.apply(x, y0)
-    fused = parallel.FusedShardedHeff(D.C128, 4, chi, chi - 16, [(L, Wc, R)], ws, 0, 1)
+    fused = parallel.FusedShardedHeff(D.C128, 4, chi, chi - 16, [(L, Wc, R)], ws, 0, 1, mode=mode)
     y1 = torch.empty_like(x)
     for _ in range(3):                      # epochs advance; buffers are re-used
         fused.apply(x, y1)
