@@ -252,6 +252,14 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
     host_in = not is_dev(mpsL[0][0])
     mpsL = [[ctx.dev(t) for t in M] for M in mpsL]
     F = [[ctx.dev(t) for t in Fm] for Fm in F]
+    # The gauge site carries the norm of the whole state; for the random start of a long chain it is ~1e-195
+    # (N=200: entries 1e-2 per site, mps_tools.py:216-235) and its SQUARE underflows in the solver's first
+    # normalisation (the reference divides by zero there too).  The norm of an eigenvector guess is arbitrary:
+    # rescale it once, max-abs first so that nothing under- or overflows.
+    for M in mpsL:
+        t = M[gaugeSiteLoad]
+        t = t / torch.clamp(t.abs().max(), min=1e-300)
+        M[gaugeSiteLoad] = t / torch.linalg.vector_norm(t)
     kw = dict(nStates=nStates, alg=alg, preserveState=preserveState, orthonormalize=orthonormalize, ctx=ctx,
               stats=stats, **solver)
     cont, iterCnt, E_prev = True, 0, 0

@@ -36,9 +36,17 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     # m[(k,n),(q,s)] = psi[n,q,k,s]      (mps_tools.py:105-107)
     D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
     kfull = min(rows, cols)
-    U, S, Vh, info = D.svd(m, ctx.svd_ws, ctx.svd_method_for(rows, cols), keep=min(int(mbd), kfull))
-    Sh = S.cpu().numpy()                                        # sync; also validates the factorisation
-    if int(info.item()) != 0:
+    first = ctx.svd_method_for(rows, cols)
+    # cuSOLVER's QR-iteration gesvd occasionally reports non-converged superdiagonals (info > 0) on small
+    # rank-deficient cuts (seen on the N=200 Heisenberg ramp); the one-sided Jacobi gesvdj, then the Gram
+    # route, take over before giving up
+    for method in [first] + [mth for mth in (D.SVD_GESVDJ, D.SVD_GRAM) if mth != first]:
+        mm = m if method == D.SVD_GRAM else m.clone()           # gesvd / gesvdj destroy their input
+        U, S, Vh, info = D.svd(mm, ctx.svd_ws, method, keep=min(int(mbd), kfull))
+        Sh = S.cpu().numpy()                                    # sync; also validates the factorisation
+        if int(info.item()) == 0 and np.all(np.isfinite(Sh)):
+            break
+    else:
         raise ArithmeticError("cuSOLVER SVD did not converge (info=%d)" % int(info.item()))
     k = min(int(mbd), kfull)
     EE, EEs, Sn = calc_entanglement(Sh[:k])

@@ -63,5 +63,11 @@ if "cfg2" in which:
     print("cfg2: TASEP N=100 chi=1024 c128 two-site, one sweep after a [16,64,256] ramp", flush=True)
     out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", int(os.environ.get("PDMRG_CFG2_SWEEPS", "3")),
                                sched=[16, 64, 256])
+if "cfg4" in which:
+    print("cfg4: Heisenberg N=200 chi=2048 f64 two-site (HBM-sizing stress), sweeps after a [16,64,256] ramp", flush=True)
+    torch.cuda.reset_peak_memory_stats()
+    out["cfg4"] = timed_sweeps(M.heisenberg_mpo(200), 2048, "f64", int(os.environ.get("PDMRG_CFG4_SWEEPS", "2")), sched=[16, 64, 256])
+    out["cfg4"]["peak_hbm_gb"] = torch.cuda.max_memory_allocated() / 1e9
+    print("   peak HBM %.1f GB" % out["cfg4"]["peak_hbm_gb"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/run_configs.json", "w"), indent=1)
