@@ -483,3 +483,15 @@ def test_full_rank_split(P, ctx, direction, dims):
     assert np.max(np.abs(Am @ Bm - m)) < 1e-12 * np.abs(m).max() * cols
     iso = Am if direction == "right" else Bm.conj().T
     assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12
+
+
+def test_long_chain_random_start_norm_underflow(P):
+    """N=200: the random start's norm (~1e-195) sits on the gauge site and its square underflows in the first
+    normalisation of the local solver (the reference divides by zero there); run_sweeps rescales the gauge
+    tensor once, so the run must stay finite and give a sensible Heisenberg energy per site."""
+    mpo = P.mpo.heisenberg_mpo(200)
+    np.random.seed(0)
+    out = P.dmrg.run_dmrg(mpo, mbd=8, tol=1e-6, maxIter=1, twoSite=True, dtype="f64")
+    E = float(np.real(out[0]))
+    assert np.isfinite(E) and np.isfinite(out[1])
+    assert 0.43 < abs(E) / 200 < 0.45          # open-chain E/N -> -0.4431 (sign convention of Hfun: -H)
