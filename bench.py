@@ -538,18 +538,20 @@ def cpu_baseline(args):
 
 def scan_sample():
     """s-points/hour on one GPU from a bounded sample of BASELINE configs[3] (ASEP N=50, chi=256 two-site,
-    s in [-0.5, 0.5]): two scan points, each cold-started through a [16, 64] chi ramp."""
+    64 s-values in [-0.5, 0.5]): four points spread over the range (the cost of a point varies 3x with s: the
+    s = -0.5 end needs ~22k mat-vecs, the middle ~4.5k), each cold-started through a [16, 64] chi ramp."""
     import torch
     from pydmrg_b200 import mpo as M, scan
-    s_vals = np.linspace(-0.5, 0.5, 64)[:2]
+    idx = [0, 21, 42, 63]
+    s_vals = np.linspace(-0.5, 0.5, 64)[idx]
     mpo_of = lambda s: M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
     np.random.seed(0)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = scan.run_scan(mpo_of, s_vals, 256, maxIter=3, tol=1e-8)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     per = float(np.mean(res["sec"]))
-    return {"config": "ASEP N=50 chi=256 two-site, 2 of 64 s-points, each cold through a [16,64] chi ramp, tol 1e-8",
-            "sec_per_point": res["sec"], "s_points_per_hour_per_gpu": 3600.0 / per,
+    return {"config": "ASEP N=50 chi=256 two-site, points %s of 64 s-values, each cold through a [16,64] chi ramp, tol 1e-8" % idx,
+            "s": [float(v) for v in s_vals], "sec_per_point": res["sec"], "s_points_per_hour_per_gpu": 3600.0 / per,
             "E": [float(np.real(e)) for e in res["E"]], "E_imag_max": float(np.max(np.abs(np.imag(res["E"]))))}
 
 

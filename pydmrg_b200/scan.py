@@ -27,6 +27,11 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     Ritz value can leave the Perron branch of these non-Hermitian generators after a warm start
     (observed at N=50, chi=256), so it is opt-in.
 
+    The default ramp (16, 64) was the best of (16,64), (64,), (32,), (8,32,128), (16,64,128) at N=50,
+    chi=256 (skipping the chi=16 stage doubles the mat-vec count at s=-0.5); capping the Davidson cycles
+    per bond in the ramp was tried and rejected (the final stage then needs 15-40x more mat-vecs and can
+    settle on the wrong branch of the non-Hermitian generator).
+
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
     rank's points, block: (lo, hi))."""
     from .dmrg import run_dmrg
