@@ -21,11 +21,19 @@ def scan_block(n_points, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_scan(local_values, n_points, rank, world, dist=None):
+def scan_indices(n_points, rank, world, interleave=False):
+    """Scan points owned by ``rank``: the contiguous block of scan_block, or -- for cold-started scans, whose
+    cost per point varies smoothly (3x) along the scan -- every ``world``-th point, which balances the ranks."""
+    if interleave:
+        return list(range(rank, n_points, world))
+    lo, hi = scan_block(n_points, rank, world)
+    return list(range(lo, hi))
+
+
+def gather_scan(local_values, n_points, rank, world, dist=None, interleave=False):
     """All ranks receive the full array of scan results (complex128)."""
     out = np.zeros(n_points, dtype=np.complex128)
-    lo, hi = scan_block(n_points, rank, world)
-    out[lo:hi] = np.asarray(local_values, dtype=np.complex128)
+    out[scan_indices(n_points, rank, world, interleave)] = np.asarray(local_values, dtype=np.complex128)
     if world == 1 or dist is None:
         return out
     import torch

@@ -2,9 +2,10 @@
 
 The reference's scan scripts are serial continuations -- every point warm-starts from the previous
 point's saved MPS (pydmrg/scripts/asep/current/bondDimConv.py:19-27, multipleStates.py:114-129).
-Here the list of points is cut into ``world`` contiguous blocks (one per GPU / rank); the
-continuation is kept INSIDE a block (first point of a block cold-starts through the chi ramp), so
-there is no data-path communication at all; results are gathered once at the end.
+Here the points are dealt to the ranks (one rank per GPU): every ``world``-th point for the default
+cold-started scan (the cost of a point varies 3x along the scan, so this balances the ranks), or
+contiguous blocks with the continuation kept INSIDE a block (``continuation=True``).  Either way there
+is no data-path communication at all; results are gathered once at the end.
 
     torchrun --nproc-per-node 8 -m pydmrg_b200.scan --N 50 --chi 256 --points 64
 """
@@ -13,7 +14,7 @@ import time
 import numpy as np
 
 from . import mpo as mpo_lib
-from .parallel import gather_scan, scan_block
+from .parallel import gather_scan, scan_indices
 
 
 def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
@@ -33,13 +34,14 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     settle on the wrong branch of the non-Hermitian generator).
 
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
-    rank's points, block: (lo, hi))."""
+    rank's points, points: their indices)."""
     from .dmrg import run_dmrg
     n = len(values)
-    lo, hi = scan_block(n, rank, world)
+    interleave = not continuation          # cold starts: every world-th point (balanced); continuation: blocks
+    mine = scan_indices(n, rank, world, interleave)
     E_loc, EE_loc, secs = [], [], []
     prev = None
-    for idx in range(lo, hi):
+    for idx in mine:
         mpo = mpo_of(values[idx])
         t0 = time.perf_counter()
         if prev is None or not continuation:
@@ -60,8 +62,8 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
         secs.append(time.perf_counter() - t0)
         E_loc.append(out[0]); EE_loc.append(out[1])
         prev = out[-1]
-    return {"E": gather_scan(E_loc, n, rank, world, dist), "EE": gather_scan(EE_loc, n, rank, world, dist),
-            "sec": secs, "block": (lo, hi)}
+    return {"E": gather_scan(E_loc, n, rank, world, dist, interleave), "EE": gather_scan(EE_loc, n, rank, world, dist, interleave),
+            "sec": secs, "points": mine}
 
 
 def _grow(mpsList, chi):

@@ -19,6 +19,20 @@ def test_scan_blocks_cover_everything():
         assert seen == list(range(n))
 
 
+def test_scan_indices_interleaved_and_gather():
+    """Interleaved assignment covers every point once, is balanced to within one point, and gather_scan puts
+    each rank's values back at its own indices."""
+    from pydmrg_b200.parallel import gather_scan, scan_indices
+    for n, world in ((64, 8), (50, 8), (7, 3), (3, 8)):
+        owned = [scan_indices(n, r, world, interleave=True) for r in range(world)]
+        assert sorted(i for o in owned for i in o) == list(range(n))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+        assert [scan_indices(n, r, world) for r in range(world)][0][0] == 0
+    mine = scan_indices(7, 1, 3, interleave=True)
+    full = gather_scan([float(i) for i in mine], 7, 1, 3, None, interleave=True)     # no dist: only own slots filled
+    assert [full[i].real for i in mine] == [float(i) for i in mine] and full[0] == 0
+
+
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_block_partition_is_a_partition(world):
     from pydmrg_b200 import mpo as M

@@ -267,7 +267,7 @@ def test_scan_driver_matches_independent_runs(P):
     mpo_of = lambda s: P.mpo.asep_mpo(8, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
     np.random.seed(0)
     one = scan.run_scan(mpo_of, s_vals, 16, ramp=(4,), tol=1e-11, maxIter=6, res_tol=1e-11, continuation=True)
-    assert one["block"] == (0, 4) and one["E"].shape == (4,)
+    assert one["points"] == [0, 1, 2, 3] and one["E"].shape == (4,)
     # reference values: dense ED of each point
     from oracle import dmrg_oracle as orc
     for k, s in enumerate(s_vals):
@@ -285,7 +285,7 @@ def test_scan_driver_matches_independent_runs(P):
     np.random.seed(0)
     r0 = scan.run_scan(mpo_of, s_vals, 16, rank=0, world=2, ramp=(4,), tol=1e-11, maxIter=6, res_tol=1e-11)
     r1 = scan.run_scan(mpo_of, s_vals, 16, rank=1, world=2, ramp=(4,), tol=1e-11, maxIter=6, res_tol=1e-11)
-    assert r0["block"] == (0, 2) and r1["block"] == (2, 4)
+    assert r0["points"] == [0, 2] and r1["points"] == [1, 3]           # cold starts are dealt round-robin
     both = r0["E"] + r1["E"]
     assert np.allclose(both, one["E"], rtol=1e-9, atol=1e-9)
 
