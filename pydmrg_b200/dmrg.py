@@ -61,8 +61,9 @@ class _Tick:
 # ---------------------------------------------------------------------------------------
 # renormalisation wrappers with the reference's signatures
 # ---------------------------------------------------------------------------------------
-def renormalizeR(mpsL, v, site, nStates=1, targetState=0, ctx=None):
-    """dmrg.py:49-91."""
+def renormalizeR(mpsL, v, site, nStates=1, targetState=0, ctx=None, fast=False):
+    """dmrg.py:49-91.  ``fast``: single state and the entanglement spectrum of this site is not needed --
+    ordered QR instead of the RDM eigen-decomposition (same isometry up to the bond gauge)."""
     ctx = ctx or default_context()
     proto = mpsL[0][site]
     shape = tuple(proto.shape)
@@ -72,15 +73,15 @@ def renormalizeR(mpsL, v, site, nStates=1, targetState=0, ctx=None):
     n_avg = min(nStates, V.shape[1])
     psis = [V[:, i].contiguous() for i in range(n_avg)]
     nxts = [ctx.dev(mpsL[s][site + 1]) for s in range(nStates)]
-    A, new_next, EE, EEs = rdm_renormalize_right(psis, shape, nxts, ctx, n_avg)
+    A, new_next, EE, EEs = rdm_renormalize_right(psis, shape, nxts, ctx, n_avg, fast=fast)
     for s in range(nStates):
         mpsL[s][site] = like(A, proto)
         mpsL[s][site + 1] = like(new_next[s], proto)
     return mpsL, EE, EEs
 
 
-def renormalizeL(mpsL, v, site, nStates=1, targetState=0, ctx=None):
-    """dmrg.py:93-136."""
+def renormalizeL(mpsL, v, site, nStates=1, targetState=0, ctx=None, fast=False):
+    """dmrg.py:93-136 (``fast`` as in renormalizeR)."""
     ctx = ctx or default_context()
     proto = mpsL[0][site]
     shape = tuple(proto.shape)
@@ -90,7 +91,7 @@ def renormalizeL(mpsL, v, site, nStates=1, targetState=0, ctx=None):
     n_avg = min(nStates, V.shape[1])
     psis = [V[:, i].contiguous() for i in range(n_avg)]
     prvs = [ctx.dev(mpsL[s][site - 1]) for s in range(nStates)]
-    B, new_prev, EE, EEs = rdm_renormalize_left(psis, shape, prvs, ctx, n_avg)
+    B, new_prev, EE, EEs = rdm_renormalize_left(psis, shape, prvs, ctx, n_avg, fast=fast)
     for s in range(nStates):
         mpsL[s][site] = like(B, proto)
         mpsL[s][site - 1] = like(new_prev[s], proto)
@@ -101,23 +102,24 @@ def renormalizeL(mpsL, v, site, nStates=1, targetState=0, ctx=None):
 # steps (the drop-in seam)
 # ---------------------------------------------------------------------------------------
 def rightStep(mpsL, W, F, site, nStates=1, alg="davidson", preserveState=False, orthonormalize=False,
-              ctx=None, stats=None, **solver):
-    """dmrg.py:138-148: solve at ``site``, renormalise to the right, grow the left block."""
+              ctx=None, stats=None, fast_renorm=False, **solver):
+    """dmrg.py:138-148: solve at ``site``, renormalise to the right, grow the left block.
+    ``fast_renorm`` (set by the sweeps for the sites whose EE is not reported): see renormalizeR."""
     ctx = ctx or default_context()
     E, v, ovlp = calc_eigs(mpsL, W, F, site, nStates, alg=alg, preserveState=preserveState,
                            orthonormalize=orthonormalize, ctx=ctx, stats=stats, **solver)
-    mpsL, EE, EEs = renormalizeR(mpsL, v, site, nStates=nStates, ctx=ctx)
+    mpsL, EE, EEs = renormalizeR(mpsL, v, site, nStates=nStates, ctx=ctx, fast=fast_renorm and nStates == 1)
     F = update_envR(mpsL[0], W, F, site, ctx=ctx)
     return E, mpsL, F, EE, EEs
 
 
 def leftStep(mpsL, W, F, site, nStates=1, alg="davidson", preserveState=False, orthonormalize=False,
-             ctx=None, stats=None, **solver):
+             ctx=None, stats=None, fast_renorm=False, **solver):
     """dmrg.py:174-184."""
     ctx = ctx or default_context()
     E, v, ovlp = calc_eigs(mpsL, W, F, site, nStates, alg=alg, preserveState=preserveState,
                            orthonormalize=orthonormalize, ctx=ctx, stats=stats, **solver)
-    mpsL, EE, EEs = renormalizeL(mpsL, v, site, nStates=nStates, ctx=ctx)
+    mpsL, EE, EEs = renormalizeL(mpsL, v, site, nStates=nStates, ctx=ctx, fast=fast_renorm and nStates == 1)
     F = update_envL(mpsL[0], W, F, site, ctx=ctx)
     return E, mpsL, F, EE, EEs
 
@@ -161,7 +163,7 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
 # sweeps
 # ---------------------------------------------------------------------------------------
 def rightSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=False, startSite=None,
-               endSite=None, orthonormalize=False, ctx=None, stats=None, **solver):
+               endSite=None, orthonormalize=False, ctx=None, stats=None, fast_renorm=False, **solver):
     """dmrg.py:150-172."""
     N = len(mpsL[0])
     startSite = 0 if startSite is None else startSite
@@ -170,7 +172,8 @@ def rightSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=Fal
     _log(1, "Right Sweep {}".format(iterCnt))
     for site in range(startSite, endSite):
         E, mpsL, F, _EE, _EEs = rightStep(mpsL, W, F, site, nStates, alg=alg, preserveState=preserveState,
-                                          orthonormalize=orthonormalize, ctx=ctx, stats=stats, **solver)
+                                          orthonormalize=orthonormalize, ctx=ctx, stats=stats,
+                                          fast_renorm=fast_renorm and site != N // 2, **solver)
         _log(2, "\tEnergy at Site {}: {}".format(site, E))
         if site == N // 2:
             Ereturn, EE, EEs = E, _EE, _EEs
@@ -178,7 +181,7 @@ def rightSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=Fal
 
 
 def leftSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=False, startSite=None,
-              endSite=None, orthonormalize=False, ctx=None, stats=None, **solver):
+              endSite=None, orthonormalize=False, ctx=None, stats=None, fast_renorm=False, **solver):
     """dmrg.py:186-208."""
     N = len(mpsL[0])
     startSite = N - 1 if startSite is None else startSite
@@ -187,7 +190,8 @@ def leftSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=Fals
     _log(1, "Left Sweep {}".format(iterCnt))
     for site in range(startSite, endSite, -1):
         E, mpsL, F, _EE, _EEs = leftStep(mpsL, W, F, site, nStates, alg=alg, preserveState=preserveState,
-                                         orthonormalize=orthonormalize, ctx=ctx, stats=stats, **solver)
+                                         orthonormalize=orthonormalize, ctx=ctx, stats=stats,
+                                         fast_renorm=fast_renorm and site != N // 2, **solver)
         _log(2, "\tEnergy at Site {}: {}".format(site, E))
         if site == N // 2:
             Ereturn, EE, EEs = E, _EE, _EEs
@@ -261,7 +265,7 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
         t = t / torch.clamp(t.abs().max(), min=1e-300)
         M[gaugeSiteLoad] = t / torch.linalg.vector_norm(t)
     kw = dict(nStates=nStates, alg=alg, preserveState=preserveState, orthonormalize=orthonormalize, ctx=ctx,
-              stats=stats, **solver)
+              stats=stats, fast_renorm=bool(recycle), **solver)
     cont, iterCnt, E_prev = True, 0, 0
     conv = False
     S = None

@@ -296,7 +296,26 @@ def _spectrum_from_rdm(w, keep):
     return calc_entanglement(np.sqrt(lam))
 
 
-def rdm_renormalize_right(psis, shape, nxts, ctx, n_avg=None):
+def _range_basis(X, ctx):
+    """Orthonormal basis of the column space of X (nn, c) and the coefficients C = Q^H X, without a spectrum:
+    returns (Pt (keep, nn) with rows conj(q_a), C (keep, c), row norms of C) or None.  For ONE state the
+    reference's one-site renormalisation (RDM eigenvectors, dmrg.py:64-81) keeps Dr vectors of a rank-<=Dr
+    matrix: nothing is discarded, every orthonormal basis of the range is the same isometry up to the gauge on
+    the bond, so an ordered QR (pdmrg_recycle_basis with the identity as previous basis) replaces the
+    (d*chi)^3 eigen-decomposition."""
+    nn, c = X.shape
+    if nn <= c:
+        Pt = torch.eye(nn, dtype=ctx.tdtype, device=ctx.device)
+        return Pt, X, torch.linalg.vector_norm(X, dim=1).cpu().numpy()
+    Xt = ctx.empty(c, nn)
+    D.permute4(X, Xt, (c, nn), (1, c))
+    Pt, Ct, Sh, ok, _ = D.recycle_basis(X, Xt, torch.eye(c, dtype=ctx.tdtype, device=ctx.device), c, 0, ctx.svd_ws)
+    if not ok or not np.any(Sh > 0):
+        return None
+    return Pt, Ct, Sh
+
+
+def rdm_renormalize_right(psis, shape, nxts, ctx, n_avg=None, fast=False):
     """renormalizeR, dmrg.py:49-91: equal-weight RDM over ``psis`` (state averaging, :56-66),
     eigenvectors (Hermitian solver instead of the reference's general eig -- the RDM is
     Hermitian PSD), top-Dr kept; A <- eigenvectors; neighbour <- (A^dagger psi) . M[site+1] (:90).
@@ -304,6 +323,27 @@ def rdm_renormalize_right(psis, shape, nxts, ctx, n_avg=None):
     d, Dl, Dr = shape
     nn = Dl * d
     n_avg = len(psis) if n_avg is None else n_avg
+    if fast and n_avg == 1:
+        # single state, spectrum not needed at this site: QR instead of the RDM eigen-decomposition
+        Mi = ctx.empty(nn, Dr)
+        D.permute4(psis[0], Mi, (Dl, d, Dr), (Dr, Dl * Dr, 1))
+        rb = _range_basis(Mi, ctx)
+        if rb is not None:
+            Pt, C1, Sh = rb
+            keep = min(Dr, nn)
+            EE, EEs, _ = calc_entanglement(Sh[:keep])             # row norms of C, NOT Schmidt values
+            A = ctx.empty(d, Dl, keep)
+            D.permute4(Pt, A, (d, Dl, keep), (1, d, nn), conj=True)   # A[n,kl,a] = q_a[kl*d+n] = conj(Pt[a, kl*d+n])
+            new_next = []
+            for nxt in nxts:
+                dn, Dk, Dj = nxt.shape
+                Nt = ctx.empty(dn, Dj, Dk)
+                D.permute4(nxt, Nt, (dn, Dj, Dk), (Dk * Dj, 1, Dj))
+                out = ctx.empty(dn, keep, Dj)
+                D.gemm_nt(C1, Nt, out, M=keep, N=Dj, K=Dk, batch=dn, lda=Dk, ldb=Dk, ldc=Dj, strideA=0,
+                          strideB=Dj * Dk, strideC=keep * Dj)
+                new_next.append(out)
+            return A, new_next, EE, EEs
     Ms = []
     rho = ctx.empty(nn, nn)
     for i in range(n_avg):
@@ -343,11 +383,28 @@ def rdm_renormalize_right(psis, shape, nxts, ctx, n_avg=None):
     return A, new_next, EE, EEs
 
 
-def rdm_renormalize_left(psis, shape, prvs, ctx, n_avg=None):
+def rdm_renormalize_left(psis, shape, prvs, ctx, n_avg=None, fast=False):
     """renormalizeL, dmrg.py:93-136.  Returns B, [new previous-site tensors], EE, EEs."""
     d, Dl, Dr = shape
     nn = d * Dr
     n_avg = len(psis) if n_avg is None else n_avg
+    if fast and n_avg == 1:
+        Mt = ctx.empty(nn, Dl)
+        D.permute4(psis[0], Mt, (d, Dr, Dl), (Dl * Dr, 1, Dr))
+        rb = _range_basis(Mt, ctx)
+        if rb is not None:
+            Pt, Ct, Sh = rb
+            keep = min(Dl, nn)
+            EE, EEs, _ = calc_entanglement(Sh[:keep])             # row norms of C, NOT Schmidt values
+            B = ctx.empty(d, keep, Dr)
+            D.permute4(Pt, B, (d, keep, Dr), (Dr, nn, 1), conj=True)   # B[n,a,s] = q_a[(n,s)]
+            new_prev = []
+            for prv in prvs:
+                dp, Di, Dk = prv.shape
+                out = ctx.empty(dp, Di, keep)
+                D.gemm_nt(prv, Ct, out, M=dp * Di, N=keep, K=Dk, lda=Dk, ldb=Dk, ldc=keep)   # dmrg.py:135
+                new_prev.append(out)
+            return B, new_prev, EE, EEs
     Mts = []
     rho = ctx.empty(nn, nn)
     for i in range(n_avg):

@@ -495,3 +495,22 @@ def test_long_chain_random_start_norm_underflow(P):
     E = float(np.real(out[0]))
     assert np.isfinite(E) and np.isfinite(out[1])
     assert 0.43 < abs(E) / 200 < 0.45          # open-chain E/N -> -0.4431 (sign convention of Hfun: -H)
+
+
+@pytest.mark.parametrize("dtype,model", [("c128", "asep"), ("f64", "heisenberg")])
+@pytest.mark.parametrize("N,mbd,rtol", [(10, 32, 1e-10), (14, 24, 1e-8)])
+def test_one_site_fast_renormalisation_matches_rdm_route(P, dtype, model, N, mbd, rtol):
+    """One-site sweeps (the reference's finite algorithm) with the QR renormalisation at the sites whose
+    spectrum is not reported vs the RDM eigen-decomposition everywhere.  With exact bond dimensions
+    (N=10, mbd=32) the kept basis is unique up to the gauge and the runs agree to 1e-10.  When chi
+    truncates (N=14, mbd=24) some bonds are rank deficient; the completion of the basis by zero-weight
+    vectors is arbitrary in BOTH routes (LAPACK's null vectors vs the QR's) and decides which directions
+    the next one-site update can grow into, so the two converged runs differ at the 1e-10 level."""
+    prm = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)
+    mpo = P.mpo.asep_mpo(N, prm) if model == "asep" else P.mpo.heisenberg_mpo(N)
+    res = {}
+    for rec in (False, True):
+        np.random.seed(6)
+        res[rec] = P.dmrg.run_dmrg(mpo, mbd=mbd, tol=0.0, maxIter=8, dtype=dtype, recycle=rec, res_tol=1e-12, returnEntSpec=True)
+    assert abs(res[True][0] - res[False][0]) < rtol * abs(res[False][0])
+    assert abs(res[True][1] - res[False][1]) < 100 * rtol

@@ -63,6 +63,18 @@ if "cfg2" in which:
     print("cfg2: TASEP N=100 chi=1024 c128 two-site, one sweep after a [16,64,256] ramp", flush=True)
     out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", int(os.environ.get("PDMRG_CFG2_SWEEPS", "3")),
                                sched=[16, 64, 256])
+if "onesite" in which:
+    print("one-site (the reference's finite algorithm): ASEP N=50, mbd=[16,64,256], 2 sweeps per stage", flush=True)
+    mpo = M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))
+    out["onesite"] = {}
+    for rec in (False, True):
+        np.random.seed(0); st = {}
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = dmrg.run_dmrg(mpo, mbd=[16, 64, 256], tol=1e-10, maxIter=2, recycle=rec, stats=st)
+        torch.cuda.synchronize()
+        out["onesite"]["qr_renorm" if rec else "rdm_renorm"] = {"sec": time.perf_counter() - t0, "E": [float(np.real(e)) for e in np.atleast_1d(r[0])],
+                                                               "n_matvec": st.get("n_matvec")}
+        print("   ", "QR renormalisation" if rec else "RDM eigen-decomposition", out["onesite"]["qr_renorm" if rec else "rdm_renorm"], flush=True)
 if "cfg4" in which:
     print("cfg4: Heisenberg N=200 chi=2048 f64 two-site (HBM-sizing stress), sweeps after a [16,64,256] ramp", flush=True)
     torch.cuda.reset_peak_memory_stats()
