@@ -1,5 +1,9 @@
 """Throughput of P concurrent scan workers sharing ONE GPU (development probe): the small-chi stages of a cold
-scan point are launch-latency bound, so independent points can overlap on the same device."""
+scan point are launch-latency bound, so independent points might overlap on the same device.
+
+Measured (B200, no MPS daemon): P=1 535 points/hour, P=2 381, P=4 385, P=8 386 -- separate processes are
+time-sliced by the driver at a granularity far above a Davidson cycle, so sharing a GPU between processes
+LOSES throughput.  One rank per GPU it is (concurrency inside one process would need a re-entrant library)."""
 import sys, time, os
 import multiprocessing as mp
 import numpy as np
