@@ -314,13 +314,20 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
 def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, maxIter=10, minIter=0, fname=None,
              nStates=1, targetState=0, constant_mbd=False, alg="davidson", preserveState=False,
              gaugeSiteSave=None, returnState=False, returnEnv=False, returnEntSpec=False, orthonormalize=False,
-             calcLeftState=False, *, dtype="c128", twoSite=False, ctx=None, stats=None, **solver):
+             calcLeftState=False, *, dtype="c128", twoSite=False, ctx=None, stats=None, pad_bonds=None, **solver):
     """Same call signature and return packing as pydmrg/dmrg.py:309-315 / :491-508.
     Keyword-only extensions: ``dtype`` ('c128' as the reference, or 'f64' for real problems),
-    ``twoSite`` (two-site SVD sweeps), ``stats`` (dict: mat-vec / cycle counters) and solver
-    options (``res_tol``, ``lindep``)."""
+    ``twoSite`` (two-site SVD sweeps), ``stats`` (dict: mat-vec / cycle counters), solver
+    options (``res_tol``, ``lindep``, ``max_cycle``), ``recycle`` (run_sweeps) and ``pad_bonds``:
+    whether a state carried to a larger ``mbd`` is zero-padded to it first (mps_tools.py:244-279).
+    One-site sweeps cannot grow a bond, so they always pad (the reference's behaviour); two-site sweeps
+    grow every bond by up to a factor d per visit on their own, so by default they do NOT pad -- the
+    first sweeps of a chi stage then run on the small tensors instead of on zero-filled large ones."""
     ctx = ctx or default_context(dtype)
     N = len(mpo[0])
+    if pad_bonds is None:
+        pad_bonds = not twoSite
+    grow = (lambda mL, chi: mps_tools.increase_all_mbd(mL, chi)) if pad_bonds else (lambda mL, chi: mL)
     if gaugeSiteSave is None:
         gaugeSiteSave = N // 2 + 1
     mbd = np.atleast_1d(np.asarray(mbd))
@@ -343,10 +350,10 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
         if initGuess is None:
             if mbdInd != 0 and fname is not None:
                 mpsList, gSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1))
-                mpsList = mps_tools.increase_all_mbd(mpsList, mbdi)
+                mpsList = grow(mpsList, mbdi)
                 if calcLeftState:
                     mpslList, glSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1) + "_left")
-                    mpslList = mps_tools.increase_all_mbd(mpslList, mbdi)
+                    mpslList = grow(mpslList, mbdi)
             else:
                 mpsList = mps_tools.make_all_mps_right(mps_tools.create_all_mps(N, mbdi, nStates))
                 gSite = 0
@@ -360,17 +367,17 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
             if calcLeftState:
                 mpslList, glSite = mps_tools.load_mps(initGuess + "_mbd" + str(idx) + "_left")
             if mbdInd != 0:
-                mpsList = mps_tools.increase_all_mbd(mpsList, mbdi)
+                mpsList = grow(mpsList, mbdi)
                 if calcLeftState:
-                    mpslList = mps_tools.increase_all_mbd(mpslList, mbdi)
+                    mpslList = grow(mpslList, mbdi)
         else:
             # an in-memory mpsList (lists of ndarrays), gauge at site 0 -- or (mpsList, gaugeSite)
             guess, gSite = (initGuess if (isinstance(initGuess, tuple) and len(initGuess) == 2
                                           and np.ndim(initGuess[1]) == 0) else (initGuess, 0))
             mpsList = [[np.array(t) for t in M] for M in (guess[0] if calcLeftState else guess)]
-            mpsList = mps_tools.increase_all_mbd(mpsList, mbdi)
+            mpsList = grow(mpsList, mbdi)
             if calcLeftState:
-                mpslList = mps_tools.increase_all_mbd([[np.array(t) for t in M] for M in guess[1]], mbdi)
+                mpslList = grow([[np.array(t) for t in M] for M in guess[1]], mbdi)
                 glSite = gSite
         gSite = int(gSite)
         mpsList = [[ctx.dev(t) for t in M] for M in mpsList]

@@ -55,7 +55,7 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
                     opts["res_tol"] = ramp_res_tol
                 out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
                                initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **opts)
-                guess = _grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd]))
+                guess = out[-1] if twoSite else _grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd]))
         else:
             out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,
                            dtype=dtype, returnState=True, stats=stats, **solver)

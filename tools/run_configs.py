@@ -21,7 +21,8 @@ def timed_sweeps(mpo, chi, dtype, n_sweeps, seed=0, two_site=True, sched=None, r
     if sched:
         r = dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=two_site, ctx=ctx)
         mpsL, g = mps_tools.load_mps(os.path.join(tmp, "st_mbd%d" % (len(sched) - 1)))
-        mpsL = mps_tools.increase_all_mbd(mpsL, chi)
+        if not two_site or os.environ.get("PDMRG_PAD"):          # two-site sweeps grow the bonds on their own
+            mpsL = mps_tools.increase_all_mbd(mpsL, chi)
     else:
         mpsL = mps_tools.make_all_mps_right(mps_tools.create_all_mps(N, chi, 1))
     t_prep = time.perf_counter() - t0
@@ -40,7 +41,8 @@ def timed_sweeps(mpo, chi, dtype, n_sweeps, seed=0, two_site=True, sched=None, r
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         res.append({"sweep": s, "sec": dt, "E": complex(E).real, "EE": float(EE), "n_matvec": stats.get("n_matvec"), "cycles": stats.get("cycles"),
                     "t_eig": stats.get("t_eig"), "t_svd": stats.get("t_svd"), "t_env": stats.get("t_env"),
-                    "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0)})
+                    "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0),
+                    "max_bond": int(max(t.shape[2] for t in mpsL[0]))})
         print("   sweep", res[-1], flush=True)
     return {"prep_sec": t_prep, "sweeps": res}
 
@@ -52,16 +54,16 @@ if "cfg0" in which:
     print("cfg0", out["cfg0"], flush=True)
 if "cfg1" in which:
     print("cfg1: Heisenberg N=100 chi=256 f64 two-site", flush=True)
-    out["cfg1"] = timed_sweeps(M.heisenberg_mpo(100), 256, "f64", 3, sched=[16, 64])
+    out["cfg1"] = timed_sweeps(M.heisenberg_mpo(100), 256, "f64", 5, sched=[16, 64])
 if "cfg3pt" in which:
     print("cfg3 point: ASEP N=50 chi=256 c128 one s value, two-site", flush=True)
-    out["cfg3pt"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 3, sched=[16, 64])
+    out["cfg3pt"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 5, sched=[16, 64])
 if "cfg3pt1" in which:
     print("cfg3 point: ASEP N=50 chi=256 c128 one s value, ONE-site (the reference's finite algorithm)", flush=True)
     out["cfg3pt1"] = timed_sweeps(M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)), 256, "c128", 3, two_site=False, sched=[16, 64])
 if "cfg2" in which:
     print("cfg2: TASEP N=100 chi=1024 c128 two-site, one sweep after a [16,64,256] ramp", flush=True)
-    out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", int(os.environ.get("PDMRG_CFG2_SWEEPS", "3")),
+    out["cfg2"] = timed_sweeps(M.asep_mpo(100, (0.35, 0, 1, 0, 2 / 3, 0, -0.5)), 1024, "c128", int(os.environ.get("PDMRG_CFG2_SWEEPS", "5")),
                                sched=[16, 64, 256])
 if "onesite" in which:
     print("one-site (the reference's finite algorithm): ASEP N=50, mbd=[16,64,256], 2 sweeps per stage", flush=True)
