@@ -8,6 +8,7 @@
 
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#include <cstdlib>
 #include <dlfcn.h>
 #include <mutex>
 #include <vector>
@@ -604,7 +605,12 @@ extern "C" int pdmrg_left_basis(int dtype, int n, int c, int keep, const void* X
 namespace pdmrg {
 namespace {
 
-constexpr int RECYCLE_JACOBI_MAX = 160;    // window sizes up to this use cuSOLVER's one-kernel Jacobi eigensolver
+// window sizes up to this use cuSOLVER's Jacobi eigensolver (PDMRG_JACOBI_MAX overrides, for experiments)
+int recycle_jacobi_max() {
+  static const int v = [] { const char* e = getenv("PDMRG_JACOBI_MAX"); return e ? atoi(e) : 160; }();
+  return v;
+}
+#define RECYCLE_JACOBI_MAX (recycle_jacobi_max())
 
 struct RecycleLayout {
   size_t tau, H, lam, Tw, G, lwork_bytes;
