@@ -89,6 +89,10 @@ def main():
         dist.init_process_group("nccl")
     s_vals = np.linspace(args.smin, args.smax, args.points)        # scripts/asep/current/bondDimConv.py:10
     mpo_of = lambda s: mpo_lib.asep_mpo(args.N, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    # library start-up (cuSOLVER / cuBLAS handles, allocator, NCCL) is paid once per process: keep it out of the clock
+    run_scan(lambda s: mpo_lib.asep_mpo(8, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s))), s_vals[:1], 16, ramp=(4,), maxIter=0)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
