@@ -116,3 +116,13 @@ def test_host_eig_matches_numpy(lib):
             ref = np.linalg.eigvals(a)
             assert max(min(abs(x - ref)) for x in wc) < 1e-9 * max(1.0, abs(ref).max())
             assert np.allclose(np.linalg.norm(vc, axis=0), 1.0)
+
+
+def test_recycle_window_bookkeeping():
+    """Host-side bookkeeping of the warm-started truncation: number of spare vectors per cut."""
+    from pydmrg_b200 import truncate
+    assert truncate.spare_count(1024, 2048, 2048) == 128
+    assert truncate.spare_count(256, 512, 512) == 32
+    assert truncate.spare_count(8, 64, 64) == 2                 # at least two spares ...
+    assert truncate.spare_count(60, 64, 200) == 4               # ... but never beyond the cut's rank
+    assert truncate.spare_count(64, 64, 200) == 0               # nothing is discarded: no spares, no window
