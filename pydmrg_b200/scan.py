@@ -82,8 +82,16 @@ def main():
     ap.add_argument("--smin", type=float, default=-0.5)
     ap.add_argument("--smax", type=float, default=0.5)
     ap.add_argument("--max-iter", type=int, default=4)
+    ap.add_argument("--pin-cores", action="store_true",
+                    help="give every local rank its own slice of the host cores (the scan is host-latency bound)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.pin_cores and hasattr(os, "sched_setaffinity"):
+        cores = sorted(os.sched_getaffinity(0))
+        lw, lr = int(os.environ.get("LOCAL_WORLD_SIZE", world)), int(os.environ.get("LOCAL_RANK", 0))
+        per = max(1, len(cores) // max(1, lw))
+        mine = cores[lr * per:(lr + 1) * per] or cores
+        os.sched_setaffinity(0, set(mine))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     if world > 1:
         dist.init_process_group("nccl")
@@ -102,6 +110,7 @@ def main():
         dt = float(t.item())
     if rank == 0:
         print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
+                          "host_cores": os.cpu_count(), "cores_per_rank": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
                           "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt,
                           "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
     if world > 1:
