@@ -64,12 +64,39 @@ def svd_truncate(psi, shape, mbd, ctx, absorb=None):
     return A, B, Sn, EE, EEs
 
 
-RECYCLE_FRACTION = 8        # spare vectors p = window depth b = k // RECYCLE_FRACTION (at least 2)
+RECYCLE_FRACTION = 8        # spare vectors p = window depth b = k // RECYCLE_FRACTION (at least 4)
+RECYCLE_MIN_SPARE = 4
+RECYCLE_SAFE_DISCARD = 1e-11   # below this discarded weight a bond is warm-started from its 2nd visit on, else from its 3rd
+
+
+def window_depth(k):
+    return max(RECYCLE_MIN_SPARE, k // RECYCLE_FRACTION)
 
 
 def spare_count(k, rows, cols):
     """Number of spare basis vectors carried beyond the kept k for the recycled truncation."""
-    return max(0, min(max(2, k // RECYCLE_FRACTION), min(rows, cols) - k))
+    return max(0, min(window_depth(k), min(rows, cols) - k))
+
+
+def recycle_allowed(cache, site, shape_key):
+    """A bond may be warm-started once it has been decomposed exactly AT ITS CURRENT SHAPE either once with
+    (numerically) nothing discarded, or twice.  Bases taken from a state that is still far from converged and
+    truncated leave a slowly decaying lag in the kept subspace (oracle/recycle_oracle.py: Heisenberg N=20,
+    chi=32 lags the exact-SVD sweeps by 1e-10 for six sweeps when recycling starts at the second visit, and by
+    1e-15 when it starts at the third)."""
+    st = cache.get(("state", site))
+    if st is None or st["shape"] != shape_key:
+        return False
+    return st["disc"] < RECYCLE_SAFE_DISCARD or st["exact_visits"] >= 2
+
+
+def note_exact_visit(cache, site, shape_key, disc):
+    st = cache.get(("state", site))
+    if st is None or st["shape"] != shape_key:
+        st = {"shape": shape_key, "exact_visits": 0, "disc": 1.0}
+    st["exact_visits"] += 1
+    st["disc"] = float(disc)
+    cache[("state", site)] = st
 
 
 def eig_truncate(psi, shape, mbd, ctx, direction, spare=0, extras=None):
@@ -101,7 +128,11 @@ def eig_truncate(psi, shape, mbd, ctx, direction, spare=0, extras=None):
         # the next `spare` eigenvectors seed the recycled truncation of this bond's next visit: rows u_a
         # (left vectors) after a right-moving step, rows conj(v_a) (right vectors) after a left-moving one
         extras["ext"] = Ut[k:k + spare].clone()
-    lam = np.clip(lam_dev.cpu().numpy()[:k], 0.0, None)
+    lam_all = np.clip(lam_dev.cpu().numpy(), 0.0, None)
+    lam = lam_all[:k]
+    if extras is not None:
+        tot = float(lam_all.sum())
+        extras["disc"] = float(lam_all[k:].sum() / tot) if tot > 0 else 0.0      # discarded weight of this cut
     EE, EEs, Sn = calc_entanglement(np.sqrt(lam))
     A = ctx.empty(d1, Dl, k)
     B = ctx.empty(d2, k, Dr)
@@ -146,7 +177,7 @@ def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext, method=None):
     else:
         D.permute4(warm, Wt, (k, Dl, d1), (1, k, Dl * k))           # Wt[i,(l,n)] = A0[n,l,i]
     Wt[k:].copy_(ext)
-    b = min(k, max(2, k // RECYCLE_FRACTION))
+    b = min(k, window_depth(k))
     Pt, Ct, Sh, ok, used = D.recycle_basis(X1, X2, Wt, k, b, ctx.svd_ws, method=method)
     if not ok:
         return None
@@ -236,6 +267,7 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
     p = spare_count(k, rows, cols)
     other = "left" if right else "right"
     ext = recycle.get((site, direction))
+    shape_key = (rows, cols, k)
     if not exact and k == min(rows, cols):
         r = full_rank_split(psi, shape, ctx, direction)
         if r is not None:
@@ -243,7 +275,7 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
             if stats is not None:
                 stats["n_full_rank"] = stats.get("n_full_rank", 0) + 1
             return r
-    if not exact and p > 0 and ext is not None and warm is not None:
+    if not exact and p > 0 and ext is not None and warm is not None and recycle_allowed(recycle, site, shape_key):
         top = warm[1] if right else warm[0]
         want = (d2, k, Dr) if right else (d1, Dl, k)
         if is_dev(top) and tuple(top.shape) == want and top.dtype == ctx.tdtype and ext.dtype == ctx.tdtype \
@@ -263,6 +295,7 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
     out = eig_truncate(psi, shape, mbd, ctx, direction, spare=p, extras=extras)
     if "ext" in extras:
         recycle[(site, other)] = extras["ext"]
+        note_exact_visit(recycle, site, shape_key, extras.get("disc", 1.0))
     else:
         recycle.pop((site, other), None)
     if stats is not None:

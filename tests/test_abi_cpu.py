@@ -123,6 +123,16 @@ def test_recycle_window_bookkeeping():
     from pydmrg_b200 import truncate
     assert truncate.spare_count(1024, 2048, 2048) == 128
     assert truncate.spare_count(256, 512, 512) == 32
-    assert truncate.spare_count(8, 64, 64) == 2                 # at least two spares ...
+    assert truncate.spare_count(8, 64, 64) == 4                 # at least four spares ...
     assert truncate.spare_count(60, 64, 200) == 4               # ... but never beyond the cut's rank
     assert truncate.spare_count(64, 64, 200) == 0               # nothing is discarded: no spares, no window
+    # start policy: once exactly with nothing discarded, or twice exactly, at the CURRENT shape
+    cache = {}
+    assert not truncate.recycle_allowed(cache, 7, (2048, 2048, 1024))
+    truncate.note_exact_visit(cache, 7, (2048, 2048, 1024), 1e-9)
+    assert not truncate.recycle_allowed(cache, 7, (2048, 2048, 1024))
+    truncate.note_exact_visit(cache, 7, (2048, 2048, 1024), 1e-9)
+    assert truncate.recycle_allowed(cache, 7, (2048, 2048, 1024))
+    assert not truncate.recycle_allowed(cache, 7, (2048, 2048, 512))      # the bond changed shape: start over
+    truncate.note_exact_visit(cache, 8, (512, 512, 256), 1e-20)
+    assert truncate.recycle_allowed(cache, 8, (512, 512, 256))

@@ -444,8 +444,10 @@ def test_recycled_truncate_matches_exact(P, direction, dtype):
 @pytest.mark.parametrize("model", ["heisenberg_f64", "asep_c128"])
 def test_recycled_sweeps_match_exact_sweeps(P, model):
     """Two-site sweeps with the warm-started truncation converge to the same fixed point as sweeps that
-    diagonalise every bond from scratch: E to 1e-10 relative, EE to 1e-8 (north-star tolerances), with
-    chi truncating (discarded weight ~1e-7..1e-9) and the projective path active (d*chi >= 128)."""
+    diagonalise every bond from scratch: E to 1e-10 relative, EE to 1e-8 (north-star tolerances), with the
+    projective path active (d*chi >= 128).  At these sizes (N=18, chi=64) the discarded weight is at round-off
+    level; the truncating regime is pinned on the CPU by the NumPy restatement of the same algorithm
+    (oracle/recycle_oracle.py, tests/test_oracle.py::test_recycled_truncation_reaches_the_exact_svd_fixed_point)."""
     if model == "heisenberg_f64":
         mpo, dtype, chi = P.mpo.heisenberg_mpo(18), "f64", 64
     else:
