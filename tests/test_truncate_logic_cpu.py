@@ -1,0 +1,142 @@
+"""CPU run of the HOST logic of the moving-centre truncation (pydmrg_b200/truncate.py): the device entry points
+are replaced by small torch-CPU emulations of their documented semantics, so the control flow (exact first
+visits, start policy, warm-started step, bookkeeping of the spare vectors and conjugations, tensor layouts)
+executes without a GPU.  The CUDA kernels themselves are covered by the ``-m gpu`` tests."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+
+class _Ctx:
+    tdtype = torch.complex128
+    device = torch.device("cpu")
+    svd_method = -1
+    svd_ws = None
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=self.tdtype)
+
+
+def _permute4(src, out, dims, strides, conj=False, scale=None, scale_axis=0):
+    # pdmrg_permute4: the first prod(dims) elements of `out` receive src[sum_i idx_i * stride_i] (conjugated)
+    assert all(st >= 0 for st in strides), "negative strides are not used by the paths under test"
+    view = torch.as_strided(src.reshape(-1), tuple(dims), tuple(strides))
+    res = (view.conj() if conj else view).resolve_conj().reshape(-1)
+    out.reshape(-1)[: res.numel()].copy_(res)
+    return out
+
+
+def _gemm_nt(A, B, C=None, *, M=None, N=None, K=None, batch=1, lda=None, ldb=None, ldc=None, strideA=0, strideB=0,
+             strideC=0, conjB=False, alpha=1.0, beta=0):
+    assert batch == 1 and beta == 0
+    if M is None:
+        M, K = A.shape
+        N = B.shape[0]
+        lda = ldb = K
+    a = torch.as_strided(A.reshape(-1), (M, K), (lda, 1))
+    b = torch.as_strided(B.reshape(-1), (N, K), (ldb, 1))
+    r = alpha * (a @ (b.conj() if conjB else b).T)
+    if C is None:
+        return r.contiguous()
+    ldc = N if ldc is None else ldc
+    torch.as_strided(C.reshape(-1), (M, N), (ldc, 1)).copy_(r)
+    return C
+
+
+def _left_basis(X, ws, keep=0):
+    G = X @ X.conj().T
+    lam, V = torch.linalg.eigh(G)
+    lam, V = lam.flip(0), V.flip(1)
+    return V.T.contiguous(), lam.clamp_min(0.0), torch.zeros(1, dtype=torch.int32)       # rows = eigenvectors u_a
+
+
+def _recycle_basis(X1, X2, Wt, k, b, ws, method=None):
+    from oracle import recycle_oracle as R
+    Pt, Ct, S = R.recycle_basis(X1.numpy(), X2.numpy(), Wt.numpy(), int(k), int(b))
+    return torch.from_numpy(np.ascontiguousarray(Pt)), torch.from_numpy(np.ascontiguousarray(Ct)), S, True, 1
+
+
+@pytest.fixture
+def T(monkeypatch):
+    from pydmrg_b200 import truncate, device as D
+    monkeypatch.setattr(D, "permute4", _permute4)
+    monkeypatch.setattr(D, "gemm_nt", _gemm_nt)
+    monkeypatch.setattr(D, "left_basis", _left_basis)
+    monkeypatch.setattr(D, "recycle_basis", _recycle_basis)
+    return truncate
+
+
+def _psi_and_m(rng, Dl, Dr, decay):
+    rows, cols = 2 * Dl, 2 * Dr
+    U, _ = np.linalg.qr(rng.standard_normal((rows, rows)) + 1j * rng.standard_normal((rows, rows)))
+    V, _ = np.linalg.qr(rng.standard_normal((cols, cols)) + 1j * rng.standard_normal((cols, cols)))
+    q = min(rows, cols)
+    s = np.exp(-decay * np.arange(q)); s /= np.linalg.norm(s)
+    m = (U[:, :q] * s) @ V[:, :q].conj().T
+    psi = m.reshape(Dl, 2, 2, Dr).transpose(1, 2, 0, 3).reshape(-1)
+    return torch.from_numpy(np.ascontiguousarray(psi)), m, s
+
+
+def _mat(A, B):
+    d1, Dl, k = A.shape
+    d2, _, Dr = B.shape
+    Am = A.numpy().transpose(1, 0, 2).reshape(Dl * d1, k)
+    Bm = B.numpy().transpose(1, 0, 2).reshape(k, d2 * Dr)
+    return Am, Bm
+
+
+def test_truncate_twosite_visits_and_start_policy(T):
+    """right (exact, first visit) -> left (exact: truncating state, policy wants two exact visits) -> right
+    (warm-started) -> left (warm-started): every step returns the isometry on the side left behind and the
+    exact projection of psi as centre; the warm-started steps reproduce the optimal discarded weight."""
+    rng = np.random.default_rng(0)
+    ctx = _Ctx()
+    Dl = Dr = 64                                     # rows = cols = 128: the projective path is active
+    chi = 96
+    psi, m, s = _psi_and_m(rng, Dl, Dr, 0.12)        # discarded weight ~1e-10 at k = 96: "truncating"
+    shape = (2, 2, Dl, Dr)
+    cache, stats = {}, {}
+    w_opt = float(np.sum(s[chi:] ** 2))
+    A = B = None
+    for visit, direction in enumerate(["right", "left", "right", "left"]):
+        warm = None if A is None else (A, B)
+        A, B, Sn, EE, EEs = T.truncate_twosite(psi, shape, chi, ctx, direction, recycle=cache, site=3, warm=warm, stats=stats)
+        Am, Bm = _mat(A, B)
+        iso = Am if direction == "right" else Bm.conj().T
+        assert np.max(np.abs(iso.conj().T @ iso - np.eye(chi))) < 1e-12
+        proj = iso @ (iso.conj().T @ m) if direction == "right" else (m @ iso) @ iso.conj().T
+        assert np.max(np.abs(Am @ Bm - proj)) < 1e-12
+        w = np.linalg.norm(m) ** 2 - np.linalg.norm(Am @ Bm) ** 2
+        assert abs(w - w_opt) < 1e-13
+        # the next visit of this bond is seeded with the spare rows of the side that was left behind
+        other = "left" if direction == "right" else "right"
+        assert tuple(cache[(3, other)].shape) == (T.spare_count(chi, 128, 128), 128)
+    assert stats.get("n_exact_trunc") == 2 and stats.get("n_recycled") == 2
+    assert cache[("state", 3)]["exact_visits"] == 2
+
+
+def test_truncate_twosite_immediate_recycling_when_nothing_is_discarded(T):
+    rng = np.random.default_rng(1)
+    ctx = _Ctx()
+    Dl = Dr = 64
+    chi = 96
+    psi, m, s = _psi_and_m(rng, Dl, Dr, 0.6)         # spectrum below 1e-16 long before k = 96
+    cache, stats = {}, {}
+    A, B, *_ = T.truncate_twosite(psi, (2, 2, Dl, Dr), chi, ctx, "right", recycle=cache, site=0, warm=None, stats=stats)
+    A, B, *_ = T.truncate_twosite(psi, (2, 2, Dl, Dr), chi, ctx, "left", recycle=cache, site=0, warm=(A, B), stats=stats)
+    assert stats.get("n_exact_trunc") == 1 and stats.get("n_recycled") == 1
+    Am, Bm = _mat(A, B)
+    assert np.max(np.abs(Am @ Bm - m)) < 1e-12
+
+
+def test_full_rank_split_logic(T):
+    rng = np.random.default_rng(2)
+    ctx = _Ctx()
+    for Dl, Dr, direction in ((32, 100, "right"), (100, 32, "right"), (32, 100, "left"), (100, 32, "left")):
+        psi, m, s = _psi_and_m(rng, Dl, Dr, 0.05)
+        A, B, Sn, EE, EEs = T.full_rank_split(psi, (2, 2, Dl, Dr), ctx, direction)
+        Am, Bm = _mat(A, B)
+        assert np.max(np.abs(Am @ Bm - m)) < 1e-12
+        iso = Am if direction == "right" else Bm.conj().T
+        assert np.max(np.abs(iso.conj().T @ iso - np.eye(iso.shape[1]))) < 1e-12
