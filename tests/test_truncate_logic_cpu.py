@@ -17,12 +17,20 @@ class _Ctx:
     def empty(self, *shape):
         return torch.empty(shape, dtype=self.tdtype)
 
+    def svd_method_for(self, rows, cols):
+        return 0
+
 
 def _permute4(src, out, dims, strides, conj=False, scale=None, scale_axis=0):
     # pdmrg_permute4: the first prod(dims) elements of `out` receive src[sum_i idx_i * stride_i] (conjugated)
     assert all(st >= 0 for st in strides), "negative strides are not used by the paths under test"
     view = torch.as_strided(src.reshape(-1), tuple(dims), tuple(strides))
-    res = (view.conj() if conj else view).resolve_conj().reshape(-1)
+    res = (view.conj() if conj else view).resolve_conj()
+    if scale is not None:                      # out[..., i, ...] *= scale[i] along scale_axis
+        shp = [1] * len(dims)
+        shp[scale_axis] = dims[scale_axis]
+        res = res * scale.reshape(shp).to(res.dtype)
+    res = res.reshape(-1)
     out.reshape(-1)[: res.numel()].copy_(res)
     return out
 
@@ -51,6 +59,11 @@ def _left_basis(X, ws, keep=0):
     return V.T.contiguous(), lam.clamp_min(0.0), torch.zeros(1, dtype=torch.int32)       # rows = eigenvectors u_a
 
 
+def _svd(a, ws, method=0, keep=0):
+    U, S, Vh = torch.linalg.svd(a, full_matrices=False)
+    return U.contiguous(), S.to(torch.float64), Vh.contiguous(), torch.zeros(1, dtype=torch.int32)
+
+
 def _recycle_basis(X1, X2, Wt, k, b, ws, method=None):
     from oracle import recycle_oracle as R
     Pt, Ct, S = R.recycle_basis(X1.numpy(), X2.numpy(), Wt.numpy(), int(k), int(b))
@@ -64,6 +77,7 @@ def T(monkeypatch):
     monkeypatch.setattr(D, "gemm_nt", _gemm_nt)
     monkeypatch.setattr(D, "left_basis", _left_basis)
     monkeypatch.setattr(D, "recycle_basis", _recycle_basis)
+    monkeypatch.setattr(D, "svd", _svd)
     return truncate
 
 
@@ -140,3 +154,50 @@ def test_full_rank_split_logic(T):
         assert np.max(np.abs(Am @ Bm - m)) < 1e-12
         iso = Am if direction == "right" else Bm.conj().T
         assert np.max(np.abs(iso.conj().T @ iso - np.eye(iso.shape[1]))) < 1e-12
+
+
+def test_two_site_sweeps_host_flow_with_emulated_device(T, monkeypatch):
+    """dmrg.twoSiteSweep end to end on the CPU: local solves and block updates come from the NumPy oracle, the
+    truncation runs the product's host logic over the emulated device entry points.  Checks the plumbing the GPU
+    tests cannot see from the outside: bonds are decomposed exactly until the start policy allows the warm start,
+    the centre bond stays exact, and recycled sweeps land on the energy of sweeps that never recycle."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import dmrg, device as D
+    mpo = orc.heisenberg_mpo(16)          # chi = 64: bonds 6, 7 (centre), 8 are 128 x 128 cuts, the rest below 128
+    ctx = _Ctx()
+    ctx.tdtype = torch.complex128
+
+    def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", oneSite=True, ctx=None, stats=None, **kw):
+        A0, B0 = mpsL[0][site].numpy(), mpsL[0][site + 1].numpy()
+        shape = (A0.shape[0], B0.shape[0], A0.shape[1], B0.shape[2])
+        Ls = [Fm[site].numpy() for Fm in F]; Rs = [Fm[site + 2].numpy() for Fm in F]
+        mv = lambda x: orc.heff_twosite(x, Ls, [op[site] for op in W], [op[site + 1] for op in W], Rs, shape, "blas")
+        guess = np.einsum("ijk,lkm->iljm", A0, B0).reshape(-1)
+        E, vecs, _ = orc.local_eigs(mv, [guess], 1, site, len(mpsL[0]), alg="davidson", check=False)
+        return E[0], torch.from_numpy(np.ascontiguousarray(vecs[:, :1].astype(np.complex128))), None
+
+    monkeypatch.setattr(dmrg, "calc_eigs", calc_eigs)
+    monkeypatch.setattr(D, "env_update_right", lambda A, W, L, bra, ws: torch.from_numpy(np.ascontiguousarray(
+        orc.env_update_right(A.numpy(), W, L.numpy(), None, "blas").astype(np.complex128))))
+    monkeypatch.setattr(D, "env_update_left", lambda B, W, R, bra, ws: torch.from_numpy(np.ascontiguousarray(
+        orc.env_update_left(B.numpy(), W, R.numpy(), None, "blas").astype(np.complex128))))
+    ctx.ws = None
+    ctx.dev = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.complex128)))
+    res = {}
+    for rec in (False, True):
+        np.random.seed(3)
+        mps = orc.make_mps_right(orc.random_mps(16, 64))
+        env = orc.build_env(mps, mpo, 64, gauge_site=0, mode="blas")
+        mpsL = [[ctx.dev(t) for t in mps]]
+        F = [[ctx.dev(t) for t in Fm] for Fm in env]
+        cache = {} if rec else None
+        stats_all = []
+        for sw in range(3):
+            st = {}
+            E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, 64, ctx=ctx, stats=st, recycle=cache)
+            stats_all.append(st)
+        res[rec] = (complex(E), float(EE), stats_all)
+    (E0, EE0, _), (E1, EE1, st1) = res[False], res[True]
+    assert abs(E1 - E0) < 1e-10 * abs(E0) and abs(EE1 - EE0) < 1e-8
+    assert st1[0].get("n_recycled", 0) + st1[1].get("n_recycled", 0) + st1[2].get("n_recycled", 0) > 0
+    assert all(s.get("n_exact_trunc", 0) >= 2 for s in st1)          # the centre bond, both directions, every sweep
