@@ -174,7 +174,32 @@ def runs_fixture():
             print(k, out[k])
 
 
+def multistate_fixture():
+    """Reference run_dmrg with nStates=2 (dmrg.py:309; state-averaged RDM :56-66, block Davidson with two roots,
+    gap = E[0] - E[1] :295-296) on seeded starts, plus the two leading ED eigenvalues (tools/ed.py:4)."""
+    out = {}
+    prm = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)
+    for tag, N, mbd, seed in (("asep6", 6, 8, 6), ("asep8", 8, 16, 4)):
+        mpo = ref.asep.return_mpo(N, prm)
+        u, _ = ref.ed.ed(mpo)
+        np.random.seed(seed)
+        with quiet():
+            r = ref.dmrg.run_dmrg(mpo, mbd=mbd, tol=1e-10, maxIter=6, nStates=2, returnEntSpec=True)
+        out[tag + "_E"], out[tag + "_EE"], out[tag + "_gap"], out[tag + "_EEs"] = np.array(r[0]), np.array(r[1]), np.array(r[2]), r[3]
+        out[tag + "_ed"] = np.array(u[:2])
+        out[tag + "_cfg"] = np.array([N, mbd, seed])
+    out["params"] = np.array(prm)
+    np.savez_compressed(os.path.join(HERE, "multistate.npz"), **out)
+    for k in sorted(out):
+        if out[k].size <= 3:
+            print(k, out[k])
+
+
 if __name__ == "__main__":
+    if "multistate" in sys.argv[1:]:
+        multistate_fixture()
+        sys.exit(0)
     kernels_fixture()
     davidson_fixture()
     runs_fixture()
+    multistate_fixture()
