@@ -28,7 +28,8 @@ from .core import Context, default_context, is_dev, like
 from .eigs import calc_eigs
 from .env import calc_env, update_envL, update_envR
 from .mpo import mpo_conj_trans
-from .truncate import rdm_renormalize_left, rdm_renormalize_right, svd_truncate, truncate_twosite
+from .truncate import (rdm_renormalize_left, rdm_renormalize_right, rdm_truncate_twosite_states, svd_truncate,
+                       truncate_twosite)
 
 VERBOSE = 0
 
@@ -131,22 +132,36 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
     (tools/env_tools.py:40-50 / 28-38).  The singular values go to the new centre site.
     Returns (E, mpsL, F, EE, EEs, S)."""
     ctx = ctx or default_context()
-    if nStates != 1:
-        raise NotImplementedError("two-site finite sweeps target one state")
     proto = mpsL[0][site]
     d1, Dl, _ = proto.shape
     d2, _, Dr = mpsL[0][site + 1].shape
     prof = stats is not None and stats.get("profile")
     tick = _Tick(prof)
-    E, v, _ = calc_eigs(mpsL, W, F, site, 1, alg=alg, oneSite=False, edgePreserveState=False, ctx=ctx,
-                        stats=stats, return_device=True, **solver)
-    tick.lap(stats, "t_eig")
-    psi = v[:, 0].contiguous()
-    A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction, recycle=recycle, site=site,
-                                        warm=(mpsL[0][site], mpsL[0][site + 1]), exact=exact_trunc, stats=stats)
-    tick.lap(stats, "t_svd")
-    mpsL[0][site] = like(A, proto)
-    mpsL[0][site + 1] = like(B, proto)
+    if nStates != 1:
+        # several target states (SURVEY 8f.3): block Davidson on the two-site problem, then the reference's
+        # state-averaged RDM (dmrg.py:56-66) gives ONE isometry for all states; each keeps its own centre.
+        # As in the reference's one-site steps the blocks are built from mpsL[0] (dmrg.py:147,183).
+        E, v, _ = calc_eigs(mpsL, W, F, site, nStates, alg=alg, oneSite=False, edgePreserveState=False, ctx=ctx,
+                            stats=stats, return_device=True, **solver)
+        tick.lap(stats, "t_eig")
+        n_avg = min(nStates, v.shape[1])
+        psis = [v[:, i].contiguous() for i in range(n_avg)]
+        As, Bs, S, EE, EEs = rdm_truncate_twosite_states(psis, (d1, d2, Dl, Dr), mbd, ctx, direction, spectrum=exact_trunc)
+        tick.lap(stats, "t_svd")
+        for s in range(nStates):
+            mpsL[s][site] = like(As[min(s, n_avg - 1)], proto)
+            mpsL[s][site + 1] = like(Bs[min(s, n_avg - 1)], proto)
+        A, B = As[0], Bs[0]
+    else:
+        E, v, _ = calc_eigs(mpsL, W, F, site, 1, alg=alg, oneSite=False, edgePreserveState=False, ctx=ctx,
+                            stats=stats, return_device=True, **solver)
+        tick.lap(stats, "t_eig")
+        psi = v[:, 0].contiguous()
+        A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction, recycle=recycle, site=site,
+                                            warm=(mpsL[0][site], mpsL[0][site + 1]), exact=exact_trunc, stats=stats)
+        tick.lap(stats, "t_svd")
+        mpsL[0][site] = like(A, proto)
+        mpsL[0][site + 1] = like(B, proto)
     if direction == "right":
         for m in range(len(W)):
             out = D.env_update_right(A, W[m][site], ctx.dev(F[m][site]), None, ctx.ws)
@@ -198,7 +213,7 @@ def leftSweep(mpsL, W, F, iterCnt, nStates=1, alg="davidson", preserveState=Fals
     return Ereturn, mpsL, F, EE, EEs
 
 
-def twoSiteSweep(mpsL, W, F, mbd, alg="davidson", ctx=None, stats=None, sites=None, recycle=None, **solver):
+def twoSiteSweep(mpsL, W, F, mbd, alg="davidson", ctx=None, stats=None, sites=None, recycle=None, nStates=1, **solver):
     """One full two-site sweep: bonds 0..N-2 moving right, then N-2..0 moving left.
     E / EE / S are recorded at the centre bond (N//2-1, N//2).
 
@@ -209,13 +224,13 @@ def twoSiteSweep(mpsL, W, F, mbd, alg="davidson", ctx=None, stats=None, sites=No
     N = len(mpsL[0])
     E = EE = EEs = S = None
     for site in range(0, N - 1):
-        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "right", mbd, alg=alg, ctx=ctx, stats=stats, recycle=recycle,
-                                             exact_trunc=(site == N // 2 - 1), **solver)
+        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "right", mbd, nStates=nStates, alg=alg, ctx=ctx, stats=stats,
+                                             recycle=recycle, exact_trunc=(site == N // 2 - 1), **solver)
         if site == N // 2 - 1:
             E, EE, EEs, S = e, ee, ees, s
     for site in range(N - 2, -1, -1):
-        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "left", mbd, alg=alg, ctx=ctx, stats=stats, recycle=recycle,
-                                             exact_trunc=(site == N // 2 - 1), **solver)
+        e, mpsL, F, ee, ees, s = twoSiteStep(mpsL, W, F, site, "left", mbd, nStates=nStates, alg=alg, ctx=ctx, stats=stats,
+                                             recycle=recycle, exact_trunc=(site == N // 2 - 1), **solver)
         if site == N // 2 - 1:
             E, EE, EEs, S = e, ee, ees, s
     return E, mpsL, F, EE, EEs, S
@@ -272,10 +287,12 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
     if twoSite:
         if mbd is None:
             mbd = mps_tools.maxBondDim([[t for t in mpsL[0]]])
-        cache = {} if recycle else None
+        cache = {} if (recycle and nStates == 1) else None      # the warm-started truncation follows ONE state
         while cont:
-            E, mpsL, F, EE, EEs, S = twoSiteSweep(mpsL, W, F, mbd, alg=alg, ctx=ctx, stats=stats, recycle=cache, **solver)
-            cont, conv, E_prev, iterCnt = checkConv(E_prev, E, tol, iterCnt, maxIter, minIter)
+            E, mpsL, F, EE, EEs, S = twoSiteSweep(mpsL, W, F, mbd, alg=alg, ctx=ctx, stats=stats, recycle=cache,
+                                                  nStates=nStates, **solver)
+            cont, conv, E_prev, iterCnt = checkConv(E_prev, E, tol, iterCnt, maxIter, minIter, nStates=nStates,
+                                                    targetState=targetState)
         gaugeSiteSave = 0      # after a left sweep the centre is on site 0
     else:
         if gaugeSiteLoad != 0:                                  # dmrg.py:248-259

@@ -303,6 +303,71 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
     return out
 
 
+def rdm_truncate_twosite_states(psis, shape, mbd, ctx, direction, spectrum=True):
+    """Two-site truncation for SEVERAL target states: the reference's state-averaged reduced
+    density matrix (dmrg.py:56-66 / 100-110) built from the two-site wave-functions psi_s (d1,d2,Dl,Dr),
+
+      right:  rho = 1/S sum_s m_s m_s^H,  A = top-k eigenvectors (shared by all states),  B_s = A^H m_s
+      left :  rho = 1/S sum_s m_s^H m_s,  B = top-k eigenvectors^H (shared),              A_s = m_s B^H
+
+    with m_s[(Dl,d1),(d2,Dr)] (mps_tools.py:105-107): one Hermitian eigen-decomposition, every state keeps its
+    own centre tensor = the exact projection of psi_s on the kept subspace.  ``spectrum``: EE / EEs / S are
+    those of the target state psi_0 alone (dmrg.py:52), truncated to k and normalised like renorm_inf
+    (mps_tools.py:116-118); otherwise (bonds whose spectrum is not reported) they come from the averaged RDM.
+    Returns ([A_s], [B_s], S, EE, EEs).  NumPy restatement: oracle/multistate_oracle.py."""
+    d1, d2, Dl, Dr = shape
+    rows, cols = Dl * d1, d2 * Dr
+    k = min(int(mbd), rows, cols)
+    right = direction == "right"
+    nS = len(psis)
+    n = rows if right else cols
+    ms, mTs = [], []
+    rho = ctx.empty(n, n)
+    for i, psi in enumerate(psis):
+        m = ctx.empty(rows, cols)
+        D.permute4(psi, m, (Dl, d1, d2, Dr), (Dr, d2 * Dl * Dr, Dl * Dr, 1))
+        mT = ctx.empty(cols, rows)
+        D.permute4(m, mT, (cols, rows), (1, cols))
+        X, kk = (m, cols) if right else (mT, rows)              # left: eigenvectors of mT mT^H are conj(v_a)
+        D.gemm_nt(X, X, rho, M=n, N=n, K=kk, lda=kk, ldb=kk, ldc=n, conjB=True, alpha=1.0 / nS, beta=int(i > 0))
+        ms.append(m)
+        mTs.append(mT)
+    if spectrum:
+        _, S0, _, _ = D.svd(ms[0].clone(), ctx.svd_ws, ctx.svd_method_for(rows, cols))
+        EE, EEs, Sn = calc_entanglement(S0.cpu().numpy()[:k])
+    w, vec, info = D.heevd(rho, ctx.svd_ws)
+    wh = w.cpu().numpy()
+    if int(info.item()) != 0:
+        raise ArithmeticError("cuSOLVER heevd failed (info=%d)" % int(info.item()))
+    if not spectrum:
+        EE, EEs, Sn = calc_entanglement(np.sqrt(np.clip(wh[::-1][:k], 0.0, None)))
+    last = vec[n - 1]                                           # eigenvectors ascending: the top k are the LAST rows
+    As, Bs = [], []
+    if right:
+        A = ctx.empty(d1, Dl, k)
+        D.permute4(last, A, (d1, Dl, k), (1, d1, -n))           # A[p,l,a] = u_a[l*d1+p]
+        Vc = ctx.empty(k, rows)
+        D.permute4(last, Vc, (k, rows), (-n, 1), conj=True)
+        for mT in mTs:
+            C = D.gemm_nt(Vc, mT)                               # C[a,c] = sum_x conj(u_a[x]) m[x,c]
+            B = ctx.empty(d2, k, Dr)
+            D.permute4(C, B, (d2, k, Dr), (Dr, cols, 1))
+            As.append(A)
+            Bs.append(B)
+    else:
+        B = ctx.empty(d2, k, Dr)
+        D.permute4(last, B, (d2, k, Dr), (Dr, -n, 1))           # B[q,a,s] = w_a[(q,s)],  w_a = conj(v_a)
+        Wd = ctx.empty(k, cols)
+        D.permute4(last, Wd, (k, cols), (-n, 1))
+        for m in ms:
+            C = D.gemm_nt(m, Wd, conjB=True)                    # C[x,a] = sum_c m[x,c] v_a[c]
+            A = ctx.empty(d1, Dl, k)
+            D.permute4(C, A, (d1, Dl, k), (k, d1 * k, 1))
+            As.append(A)
+            Bs.append(B)
+    return As, Bs, Sn, EE, EEs
+
+
 def renorm_inf(mpsList, mpoList, envList, vecs, mbd, ctx=None):
     """Drop-in for tools/mps_tools.py:98-120 (nStates handled state by state)."""
     ctx = ctx or default_context()

@@ -1,0 +1,66 @@
+"""GPU tests of host-level features written AFTER the round's GPU budget was spent: they compose entry points
+that the validated tests already cover, their host logic runs on the CPU over emulated entry points
+(tests/test_truncate_logic_cpu.py, tests/test_parallel_cpu.py), but they have not yet executed on a B200.
+They run only when asked for,
+
+    PDMRG_RUN_PENDING=1 python -m pytest tests/test_pending_gpu.py -m gpu -q
+
+(first item of tools/round2_validate.sh); once green there they move into tests/test_sweeps_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PDMRG_RUN_PENDING") != "1",
+                                 reason="pending first run on a B200 (set PDMRG_RUN_PENDING=1)")]
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PRM = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pydmrg_b200 as pkg
+    from pydmrg_b200 import core, device, dmrg, mpo, parallel, truncate
+    return pkg
+
+
+@pytest.mark.parametrize("tag", ["asep6", "asep8"])
+def test_two_site_two_states_gap(P, tag):
+    """run_dmrg(nStates=2, twoSite=True): E and the gap against the reference's one-site nStates=2 run and
+    dense ED (tests/golden/multistate.npz, generated from the unmodified reference)."""
+    g = np.load(os.path.join(GOLD, "multistate.npz"))
+    N, mbd, seed = (int(v) for v in g[tag + "_cfg"])
+    mpo = P.mpo.asep_mpo(N, tuple(g["params"]))
+    np.random.seed(seed)
+    out = P.dmrg.run_dmrg(mpo, mbd=mbd, tol=1e-10, maxIter=6, nStates=2, twoSite=True, res_tol=1e-10)
+    E, EE, gap = out[0], out[1], out[2]
+    ed = g[tag + "_ed"]
+    assert abs(E - ed[0]) < 1e-7 * abs(ed[0])
+    assert abs(gap - (ed[0] - ed[1])) < 1e-6 * abs(ed[0])
+    assert abs(gap - g[tag + "_gap"]) < 1e-6 * abs(ed[0])
+
+
+@pytest.mark.parametrize("direction", ["right", "left"])
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+def test_state_averaged_twosite_truncation(P, direction, dtype):
+    """truncate.rdm_truncate_twosite_states on the device against its NumPy restatement."""
+    from oracle import multistate_oracle as ms
+    c = P.core.Context(dtype)
+    rng = np.random.default_rng(11)
+    shape = (2, 2, 40, 36)
+    k = 48
+    n = 4 * 40 * 36
+    rnd = (lambda: rng.standard_normal(n) + 1j * rng.standard_normal(n)) if dtype == "c128" else (lambda: rng.standard_normal(n))
+    psis = [rnd() for _ in range(2)]
+    As, Bs, Sn, EE, EEs = P.truncate.rdm_truncate_twosite_states([c.dev(p) for p in psis], shape, k, c, direction)
+    Ao, Bo, Sno, EEo, _ = ms.rdm_truncate_twosite_states(psis, shape, k, direction)
+    for s in range(2):
+        A, B = c.host(As[s]), c.host(Bs[s])
+        Am, Bm = A.transpose(1, 0, 2).reshape(80, k), B.transpose(1, 0, 2).reshape(k, 72)
+        Amo, Bmo = Ao[s].transpose(1, 0, 2).reshape(80, k), Bo[s].transpose(1, 0, 2).reshape(k, 72)
+        iso = Am if direction == "right" else Bm.conj().T
+        assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12
+        assert np.max(np.abs(Am @ Bm - Amo @ Bmo)) < 1e-10
+    assert abs(EE - EEo) < 1e-10 and np.max(np.abs(Sn - Sno)) < 1e-10

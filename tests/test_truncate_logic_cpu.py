@@ -23,8 +23,18 @@ class _Ctx:
 
 def _permute4(src, out, dims, strides, conj=False, scale=None, scale_axis=0):
     # pdmrg_permute4: the first prod(dims) elements of `out` receive src[sum_i idx_i * stride_i] (conjugated)
-    assert all(st >= 0 for st in strides), "negative strides are not used by the paths under test"
-    view = torch.as_strided(src.reshape(-1), tuple(dims), tuple(strides))
+    if all(st >= 0 for st in strides):
+        view = torch.as_strided(src.reshape(-1), tuple(dims), tuple(strides))
+    else:
+        # negative strides walk back from ``src`` (a view into a larger buffer, e.g. the last row of heevd's output)
+        base = src.as_strided((src.untyped_storage().nbytes() // src.element_size(),), (1,), 0)
+        idx = torch.full(tuple(dims), src.storage_offset(), dtype=torch.int64)
+        for ax, (n, st) in enumerate(zip(dims, strides)):
+            shp = [1] * len(dims)
+            shp[ax] = n
+            idx = idx + (torch.arange(n, dtype=torch.int64) * st).reshape(shp)
+        assert int(idx.min()) >= 0
+        view = base[idx]
     res = (view.conj() if conj else view).resolve_conj()
     if scale is not None:                      # out[..., i, ...] *= scale[i] along scale_axis
         shp = [1] * len(dims)
@@ -37,7 +47,7 @@ def _permute4(src, out, dims, strides, conj=False, scale=None, scale_axis=0):
 
 def _gemm_nt(A, B, C=None, *, M=None, N=None, K=None, batch=1, lda=None, ldb=None, ldc=None, strideA=0, strideB=0,
              strideC=0, conjB=False, alpha=1.0, beta=0):
-    assert batch == 1 and beta == 0
+    assert batch == 1 and beta in (0, 1)
     if M is None:
         M, K = A.shape
         N = B.shape[0]
@@ -48,8 +58,16 @@ def _gemm_nt(A, B, C=None, *, M=None, N=None, K=None, batch=1, lda=None, ldb=Non
     if C is None:
         return r.contiguous()
     ldc = N if ldc is None else ldc
-    torch.as_strided(C.reshape(-1), (M, N), (ldc, 1)).copy_(r)
+    out = torch.as_strided(C.reshape(-1), (M, N), (ldc, 1))
+    out.copy_(r + out if beta else r)
     return C
+
+
+def _heevd(a, ws):
+    # pdmrg_heevd: in place, row i of ``a`` <- i-th eigenvector (ascending eigenvalues)
+    w, v = torch.linalg.eigh(a)
+    a.copy_(v.T)
+    return w, a, torch.zeros(1, dtype=torch.int32)
 
 
 def _left_basis(X, ws, keep=0):
@@ -78,6 +96,7 @@ def T(monkeypatch):
     monkeypatch.setattr(D, "left_basis", _left_basis)
     monkeypatch.setattr(D, "recycle_basis", _recycle_basis)
     monkeypatch.setattr(D, "svd", _svd)
+    monkeypatch.setattr(D, "heevd", _heevd)
     return truncate
 
 
@@ -201,3 +220,78 @@ def test_two_site_sweeps_host_flow_with_emulated_device(T, monkeypatch):
     assert abs(E1 - E0) < 1e-10 * abs(E0) and abs(EE1 - EE0) < 1e-8
     assert st1[0].get("n_recycled", 0) + st1[1].get("n_recycled", 0) + st1[2].get("n_recycled", 0) > 0
     assert all(s.get("n_exact_trunc", 0) >= 2 for s in st1)          # the centre bond, both directions, every sweep
+
+
+# ---------------------------------------------------------------------------------------
+# several target states, two-site
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("direction", ["right", "left"])
+@pytest.mark.parametrize("spectrum", [True, False])
+def test_state_averaged_twosite_truncation_logic(T, direction, spectrum):
+    """truncate.rdm_truncate_twosite_states over the emulated entry points against its NumPy restatement
+    (oracle/multistate_oracle.py): shared isometry, per-state centres = exact projections, same spectrum."""
+    from oracle import multistate_oracle as ms
+    rng = np.random.default_rng(4)
+    ctx = _Ctx()
+    shape = (2, 2, 6, 5)
+    k = 7
+    psis = [rng.standard_normal(120) + 1j * rng.standard_normal(120) for _ in range(2)]
+    As, Bs, Sn, EE, EEs = T.rdm_truncate_twosite_states([torch.from_numpy(p.copy()) for p in psis], shape, k, ctx, direction,
+                                                        spectrum=spectrum)
+    Ao, Bo, Sno, EEo, EEso = ms.rdm_truncate_twosite_states(psis, shape, k, direction)
+    for s in range(2):
+        Am, Bm = _mat(As[s], Bs[s])
+        Amo = Ao[s].transpose(1, 0, 2).reshape(12, k)
+        Bmo = Bo[s].transpose(1, 0, 2).reshape(k, 10)
+        iso = Am if direction == "right" else Bm.conj().T
+        assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12
+        assert np.max(np.abs(Am @ Bm - Amo @ Bmo)) < 1e-12          # gauge-invariant: the projected wave-function
+    assert (As[0] is As[1]) if direction == "right" else (Bs[0] is Bs[1])
+    if spectrum:
+        assert abs(EE - EEo) < 1e-12 and np.max(np.abs(Sn - Sno)) < 1e-12
+    else:
+        assert np.isfinite(EE) and abs(np.sum(Sn ** 2) - 1) < 1e-12
+
+
+def test_two_site_two_state_sweeps_host_flow(T, monkeypatch):
+    """dmrg.twoSiteSweep(nStates=2) on the CPU (local solves and block updates from the oracle, the
+    state-averaged truncation through the product's host logic): both energies and the gap land on the NumPy
+    restatement's and on dense ED (fixture from the reference's tools/ed.py)."""
+    import os
+    from oracle import dmrg_oracle as orc, multistate_oracle as ms
+    from pydmrg_b200 import dmrg, device as D, mpo as M
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "multistate.npz"))
+    N, chi, seed = (int(v) for v in g["asep8_cfg"])
+    mpo = M.asep_mpo(N, tuple(g["params"]))
+    ctx = _Ctx()
+    ctx.ws = None
+    ctx.dev = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.complex128)))
+
+    def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", oneSite=True, ctx=None, stats=None, **kw):
+        A0, B0 = mpsL[0][site].numpy(), mpsL[0][site + 1].numpy()
+        shape = (A0.shape[0], B0.shape[0], A0.shape[1], B0.shape[2])
+        Ls = [Fm[site].numpy() for Fm in F]; Rs = [Fm[site + 2].numpy() for Fm in F]
+        mv = lambda x: orc.heff_twosite(x, Ls, [op[site] for op in W], [op[site + 1] for op in W], Rs, shape, "blas")
+        guesses = [np.einsum("ijk,lkm->iljm", mpsL[s][site].numpy(), mpsL[s][site + 1].numpy()).reshape(-1) for s in range(nStates)]
+        E, vecs, _ = orc.local_eigs(mv, guesses, nStates, site, len(mpsL[0]), alg="davidson", edge_preserve_state=False)
+        return E, torch.from_numpy(np.ascontiguousarray(vecs.astype(np.complex128))), None
+
+    monkeypatch.setattr(dmrg, "calc_eigs", calc_eigs)
+    monkeypatch.setattr(D, "env_update_right", lambda A, W, L, bra, ws: torch.from_numpy(np.ascontiguousarray(
+        orc.env_update_right(A.numpy(), W, L.numpy(), None, "blas").astype(np.complex128))))
+    monkeypatch.setattr(D, "env_update_left", lambda B, W, R, bra, ws: torch.from_numpy(np.ascontiguousarray(
+        orc.env_update_left(B.numpy(), W, R.numpy(), None, "blas").astype(np.complex128))))
+    np.random.seed(seed)
+    states = ms.random_states(N, chi, 2)
+    env = orc.build_env(states[0], mpo, chi, gauge_site=0, mode="blas")
+    mpsL = [[ctx.dev(t) for t in st] for st in states]
+    F = [[ctx.dev(t) for t in Fm] for Fm in env]
+    for sw in range(4):
+        E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, nStates=2)
+    np.random.seed(seed)
+    Eo, EEo = ms.run_dmrg_twosite_states(mpo, chi, 2, n_sweeps=4)[:2]
+    ed = g["asep8_ed"]
+    assert abs(E[0] - ed[0]) < 1e-7 * abs(ed[0]) and abs(E[1] - ed[1]) < 1e-7 * abs(ed[0])
+    assert abs(E[0] - Eo[0]) < 1e-9 and abs(E[1] - Eo[1]) < 1e-9 and abs(EE - EEo) < 1e-7
+    for site in range(1, N):                                   # isometries are shared, the centre (site 0) is not
+        assert mpsL[0][site] is mpsL[1][site] or torch.equal(mpsL[0][site], mpsL[1][site])
