@@ -44,6 +44,63 @@ def gather_scan(local_values, n_points, rank, world, dist=None, interleave=False
     return torch.view_as_complex(t.cpu()).numpy()
 
 
+def run_dmrg_left_right(mpo, rank, world, dist, runner=None, **kwargs):
+    """``run_dmrg(..., calcLeftState=True)`` with the right and the left eigenstate computed on different
+    ranks.  The reference runs them one after the other as two independent DMRGs -- the
+    second on ``mpo_conj_trans(mpo)``, started from a copy of the same initial state (dmrg.py:338, 369-373,
+    405, 451) -- so they shard with no data-path collective: even ranks take the right state, odd ranks the
+    left one, and one object gather at the end assembles the reference's return packing
+    ``[E, [EE, EEl], gap, ([EEs, EEsl]), ([mps, mpsl]), ([env, envl])]`` (dmrg.py:491-508; E and gap are those
+    of the right run, as in the reference) on EVERY rank.
+
+    Both ranks must draw the same initial state: seed NumPy identically before the call (the reference draws
+    one more, discarded, random MPS before copying; it has no influence on either run).  ``initGuess`` /
+    ``initEnv`` given as a ``(right, left)`` pair are split between the sides.  File-based continuation
+    (``fname`` / a string ``initGuess``) keeps the reference's naming: the left side uses ``<name>_left``.
+    ``runner`` defaults to ``pydmrg_b200.dmrg.run_dmrg`` (injectable for CPU tests of the distribution logic)."""
+    if runner is None:
+        from .dmrg import run_dmrg as runner
+    from .mpo import mpo_conj_trans
+    if world < 2:
+        return runner(mpo, calcLeftState=True, **kwargs)
+    kw = dict(kwargs)
+    kw.pop("calcLeftState", None)
+    flags = [bool(kw.get(k, False)) for k in ("returnEntSpec", "returnState", "returnEnv")]
+    side = rank % 2                                              # 0: right eigenstate, 1: left eigenstate
+    for key in ("initGuess", "initEnv"):
+        v = kw.get(key)
+        if isinstance(v, tuple) and len(v) == 2 and isinstance(v[1], (int, np.integer)) and _is_pair(v[0]):
+            kw[key] = (v[0][side], v[1])                         # ((right, left), gaugeSite)
+        elif _is_pair(v):
+            kw[key] = v[side]
+    if side == 1:
+        for key in ("fname", "initGuess"):
+            if isinstance(kw.get(key), str):
+                kw[key] = kw[key] + "_left"
+    out = None
+    if rank < 2:                                                 # ranks beyond the first pair have nothing to do
+        out = runner(mpo if side == 0 else mpo_conj_trans(mpo), **kw)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    right, left = gathered[0], gathered[1]
+    res = [right[0], [right[1], left[1]], right[2]]
+    pos = 3
+    for on in flags:
+        if on:
+            res.append([right[pos], left[pos]])
+            pos += 1
+    return res
+
+
+def _is_pair(v):
+    """(right, left) pair of MPS lists [state][site] / environments [mpoInd][k], as opposed to a single one."""
+    try:
+        return (isinstance(v, (list, tuple)) and len(v) == 2 and all(isinstance(side, (list, tuple)) for side in v)
+                and all(isinstance(side[0], (list, tuple)) and np.ndim(side[0][0]) == 3 for side in v))
+    except Exception:
+        return False
+
+
 def block_pattern(Wc, wL, wR, P):
     """Boolean (wL, wR) matrix: which (j, o) blocks of the combined local operator are non-zero."""
     B = np.abs(np.asarray(Wc).reshape(wL, P, wR, P)).max(axis=(1, 3)) > 0

@@ -86,3 +86,79 @@ def test_gather_scan_gloo_world2():
     expect = np.array([complex(i, -i) for i in range(11)])
     for rank, out in res:
         assert np.array_equal(out, expect)
+
+
+# ---------------------------------------------------------------------------------------
+# right / left eigenstates on different ranks
+# ---------------------------------------------------------------------------------------
+def _oracle_runner(mpo, mbd=8, tol=1e-10, maxIter=4, returnEntSpec=False, returnState=False, returnEnv=False, **kw):
+    """Stand-in for dmrg.run_dmrg with its return packing, computed by the NumPy oracle (CPU)."""
+    from oracle import dmrg_oracle as orc
+    np.random.seed(kw.get("seed", 5))
+    E, EE, EEs, mps, env = orc.run_dmrg_onesite(mpo, int(np.atleast_1d(mbd)[-1]), tol=tol, max_iter=maxIter)
+    out = [E, EE, None]
+    if returnEntSpec:
+        out.append(EEs)
+    if returnState:
+        out.append([mps])
+    if returnEnv:
+        out.append(env)
+    return out
+
+
+def _lr_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pydmrg_b200 import mpo as M
+    from pydmrg_b200.parallel import run_dmrg_left_right
+    mpo = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))
+    out = run_dmrg_left_right(mpo, rank, world, dist, runner=_oracle_runner, mbd=8, returnEntSpec=True, returnState=True)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_left_right_eigenstates_on_two_ranks_gloo():
+    """Rank 0 solves for the right eigenstate, rank 1 for the left one (on the conjugate-transposed MPO); every
+    rank ends with the reference's calcLeftState packing; <l|H|r>/<l|r> reproduces the eigenvalue."""
+    import torch.multiprocessing as mp
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import mpo as M
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_lr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    mpo = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))
+    right = _oracle_runner(mpo, mbd=8, returnEntSpec=True, returnState=True)
+    left = _oracle_runner(M.mpo_conj_trans(mpo), mbd=8, returnEntSpec=True, returnState=True)
+    for rank in (0, 1):
+        E, EEpair, gap, EEsPair, mpsPair = res[rank]
+        assert E == right[0] and gap is None
+        assert EEpair == [right[1], left[1]]
+        assert np.array_equal(EEsPair[0], right[3]) and np.array_equal(EEsPair[1], left[3])
+        for a, b in zip(mpsPair[0][0], right[4][0]):
+            assert np.array_equal(a, b)
+        for a, b in zip(mpsPair[1][0], left[4][0]):
+            assert np.array_equal(a, b)
+    # physics: the left state is the left eigenvector of the same eigenvalue
+    E, _, _, _, (mr, ml) = res[0]
+    lmps = [np.conj(t) for t in ml[0]]
+    num = orc.full_contract(mpo, mr[0], lmps)
+    den = orc.full_contract(None, mr[0], lmps)
+    assert abs(num / den - E) < 1e-7 * abs(E)
+    assert abs(left[0] - np.conj(right[0])) < 1e-7 * abs(E)
+
+
+def test_left_right_pair_detection():
+    from pydmrg_b200.parallel import _is_pair
+    t = np.zeros((2, 1, 2))
+    mpsList = [[t, t, t]]
+    env2 = [[t, t], [t, t]]                      # two MPO terms: a list of length two that is NOT a pair
+    assert _is_pair((mpsList, mpsList)) and _is_pair([env2, env2])
+    assert not _is_pair(mpsList) and not _is_pair(env2) and not _is_pair((mpsList, 3)) and not _is_pair(None)
