@@ -124,7 +124,7 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
 
 
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
-             res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None):
+             res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
@@ -133,6 +133,9 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     ||r||^2 <= lindep.  ``fixed_cycles``: stop after exactly that many cycles (benchmarking).
     When the H_eff ``plan`` is given the loop runs in C++ (``pdmrg_davidson``) unless
     ``native=False`` / PDMRG_PY_DAVIDSON=1; this Python loop is the specification it mirrors.
+    ``consensus``: optional callable applied to the small device arrays right before the host reads them
+    (sharded sweeps: a broadcast from rank 0, so that every rank takes the same control decisions and the
+    collectives inside ``matvec`` stay matched whatever the last bit of a reduction does).
     """
     if not isinstance(x0, (list, tuple)):
         x0 = [x0]
@@ -178,6 +181,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
             ops.dots(W.XS, space, AX[head + k], out=W.small[k * 2 * rows:])
             if head > 0:
                 ops.dots(W.AX, head, XS[head + k], out=W.small[k * 2 * rows + rows:])
+        if consensus is not None:
+            consensus(W.small[:rnow * 2 * rows])
         host = W.small[:rnow * 2 * rows].cpu().numpy()            # D2H #1 of the cycle
         for k in range(rnow):
             heff[:space, head + k] = host[k * 2 * rows: k * 2 * rows + space]
@@ -197,6 +202,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
             c = ops.dots(W.XS, space, W.R[k][:n])
             ops.project(W.XS, space, c, W.R[k][:n], scale_dev=W.norms[2 * k:2 * k + 1],
                         norm2_out=W.norms[2 * k + 1:2 * k + 2])
+        if consensus is not None:
+            consensus(W.norms[:2 * nr])
         nrm = W.norms[:2 * nr].cpu().numpy()                       # D2H #2 of the cycle
         dx2, px2 = nrm[0::2], nrm[1::2]
         if stats is not None:

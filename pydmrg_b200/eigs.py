@@ -115,13 +115,21 @@ def check_overlap(guess, vecs, E, preserveState, ctx):
 
 def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
               orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
-              fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000):
+              fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000, shard=None):
     """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
-    array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise."""
+    array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise.
+
+    ``shard`` (parallel.ShardSpec): every rank runs the same sweep on replicated tensors and the mat-vec of
+    bonds with min(Dl, Dr) >= shard.min_dim is split over the ranks (one all-reduce of y per
+    mat-vec).  The Davidson control scalars and the final eigenvectors are taken from rank 0, so the ranks
+    cannot drift apart."""
     ctx = ctx or default_context()
     own_plan = plan is None
+    sharded = None
     if own_plan:
         plan, shape = make_plan(mpsL[0], W, F, site, oneSite, ctx)
+        if shard is not None and shard.world > 1 and alg == "davidson" and min(shape[-2], shape[-1]) >= shard.min_dim:
+            sharded = shard.heff(ctx, mpsL[0], W, F, site, oneSite)
     n = plan.n
     dev_in = is_dev(mpsL[0][site]) if return_device is None else return_device
     guesses = []
@@ -131,7 +139,16 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
             guesses.append(ctx.dev(mpsL[s][site]).reshape(-1))
         else:
             guesses.append(two_site_guess(ctx.dev(mpsL[s][site]), ctx.dev(mpsL[s][site + 1]), ctx).reshape(-1))
-    if alg == "davidson":
+    if alg == "davidson" and sharded is not None:
+        vals, vecs = davidson(lambda x, y: sharded.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
+                              lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=None,
+                              native=False, max_cycle=max_cycle, consensus=shard.consensus)
+        for vk in vecs:
+            shard.consensus(vk)
+        E = -vals
+        if stats is not None:
+            stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
+    elif alg == "davidson":
         vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=plan,
                               native=native, max_cycle=max_cycle)
@@ -158,6 +175,8 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     V = torch.stack(list(vecs), dim=1)
     if own_plan:
         plan.close()
+    if sharded is not None:
+        sharded.plan.close()
     return Eout, (V if dev_in else V.cpu().numpy()), ovlp
 
 

@@ -272,6 +272,29 @@ class ShardedHeff:
         return y
 
 
+class ShardSpec:
+    """How a sweep shards its mat-vecs (passed as ``run_dmrg(..., shard=ShardSpec(rank, world, dist))``):
+    every rank runs the whole sweep on replicated tensors; the local eigenproblems of bonds with
+    min(Dl, Dr) >= ``min_dim`` use a ShardedHeff in ``mode`` ('ket': balanced for any MPO; 'bond': blocks of
+    the MPO bond) -- one NCCL all-reduce of y per mat-vec.  Truncation and block updates stay replicated."""
+
+    def __init__(self, rank, world, dist, mode="ket", min_dim=256):
+        self.rank, self.world, self.dist, self.mode = int(rank), int(world), dist, mode
+        self.min_dim = max(int(min_dim), 16 * self.world)       # every rank must own a TMA-aligned ket range
+
+    def heff(self, ctx, M, W, F, site, oneSite):
+        from .eigs import _site_ops
+        ops, P, shape = _site_ops(M, W, F, site, oneSite, ctx)
+        return ShardedHeff(ctx.code, P, shape[-2], shape[-1], ops, ctx.ws, self.rank, self.world, self.dist, mode=self.mode)
+
+    def consensus(self, t):
+        """Overwrite a small device tensor by rank 0's copy (control scalars, eigenvectors)."""
+        import torch
+        if self.world > 1:
+            self.dist.broadcast(torch.view_as_real(t) if t.is_complex() else t, src=0)
+        return t
+
+
 class FusedShardedHeff:
     """MPO-bond-sharded mat-vec whose exchange is done by the kernels themselves over peer memory
     (CUDA IPC + NVLink loads/stores): stage-C GEMM with a scatter epilogue -> flag -> reduce + all-gather

@@ -1,0 +1,84 @@
+"""Run under torchrun with N >= 2 ranks (one per GPU): two-site sweeps whose local mat-vecs are sharded over the
+ranks (run_dmrg(..., shard=ShardSpec)) against the same sweeps run unsharded on every rank.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_sharded_sweep_check.py
+
+PENDING: written after the round-1 GPU budget was spent; first run is item 2 of tools/round2_validate.sh.
+Environment: PDMRG_CHECK_CHI (default 64), PDMRG_CHECK_N (default 16), PDMRG_CHECK_TIMING=1 adds a chi=1024
+timing of one converged sweep sharded vs unsharded (TASEP N=100, BASELINE configs[2])."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    from pydmrg_b200 import dmrg, mpo as M, parallel
+    chi = int(os.environ.get("PDMRG_CHECK_CHI", "64"))
+    N = int(os.environ.get("PDMRG_CHECK_N", "16"))
+    ok = True
+    report = {"world": world, "chi": chi, "N": N}
+    for model, dtype in (("asep", "c128"), ("heisenberg", "f64")):
+        mpo = M.asep_mpo(N, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)) if model == "asep" else M.heisenberg_mpo(N)
+        res = {}
+        for mode in (None, "ket", "bond"):
+            spec = None if mode is None else parallel.ShardSpec(rank, world, dist, mode=mode, min_dim=32)
+            np.random.seed(2)                                   # identical start on every rank
+            st = {}
+            out = dmrg.run_dmrg(mpo, mbd=chi, tol=0.0, maxIter=3, twoSite=True, dtype=dtype, stats=st, res_tol=1e-11,
+                                returnEntSpec=True, shard=spec)
+            res[mode] = (complex(out[0]), float(np.real(out[1])), st.get("n_sharded_solves", 0), st.get("n_matvec", 0))
+        E0, EE0 = res[None][0], res[None][1]
+        for mode in ("ket", "bond"):
+            E, EE, ns, nmv = res[mode]
+            # every rank must hold the same numbers as rank 0
+            t = torch.tensor([E.real, E.imag, EE], dtype=torch.float64, device="cuda")
+            t0 = t.clone(); dist.broadcast(t0, 0)
+            same = bool(torch.equal(t, t0))
+            good = abs(E - E0) < 1e-10 * abs(E0) and abs(EE - EE0) < 1e-8 and ns > 0 and same
+            ok = ok and good
+            report["%s_%s" % (model, mode)] = {"dE": abs(E - E0), "dEE": abs(EE - EE0), "sharded_solves": ns,
+                                               "n_matvec": nmv, "n_matvec_unsharded": res[None][3], "same_on_all_ranks": same}
+    if os.environ.get("PDMRG_CHECK_TIMING") == "1":
+        # device-resident state as in bench.py full_sweep: ramp, then sweeps at chi; the last one is a converged sweep
+        from pydmrg_b200 import core, env as env_tools
+        ctx = core.Context("c128")
+        big = int(os.environ.get("PDMRG_CHECK_BIG_CHI", "1024"))
+        mpo = M.asep_mpo(100, (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, -0.5))
+        for mode in (None, "ket"):
+            spec = None if mode is None else parallel.ShardSpec(rank, world, dist, mode=mode)
+            np.random.seed(0)
+            out = dmrg.run_dmrg(mpo, mbd=[c for c in (16, 64, 256) if c < big], tol=1e-9, maxIter=1, twoSite=True, ctx=ctx,
+                                returnState=True)
+            mpsL = [[ctx.dev(t) for t in out[-1][0]]]
+            F = env_tools.calc_env(mpsL[0], mpo, big, gaugeSite=0, ctx=ctx)
+            cache, ts, st = {}, [], {}
+            for _ in range(5):
+                st = {}
+                torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+                E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, big, ctx=ctx, stats=st, recycle=cache, shard=spec)
+                torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+            report["sweep_sec_%s" % (mode or "unsharded")] = {"sec": ts, "n_matvec": st.get("n_matvec"), "E": [E.real, E.imag],
+                                                             "sharded_solves": st.get("n_sharded_solves", 0)}
+            del mpsL, F, cache
+            torch.cuda.empty_cache()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        report["ok"] = bool(flag.item())
+        print(json.dumps(report), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

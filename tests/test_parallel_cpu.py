@@ -162,3 +162,88 @@ def test_left_right_pair_detection():
     env2 = [[t, t], [t, t]]                      # two MPO terms: a list of length two that is NOT a pair
     assert _is_pair((mpsList, mpsList)) and _is_pair([env2, env2])
     assert not _is_pair(mpsList) and not _is_pair(env2) and not _is_pair((mpsList, 3)) and not _is_pair(None)
+
+
+# ---------------------------------------------------------------------------------------
+# sharded sweeps: wiring of calc_eigs(shard=...) (the kernels are stubbed; no GPU)
+# ---------------------------------------------------------------------------------------
+def test_calc_eigs_routes_large_bonds_through_the_sharded_matvec(monkeypatch):
+    import torch
+    from pydmrg_b200 import eigs, parallel
+
+    class FakePlan:
+        def __init__(self, n):
+            self.n, self.closed = n, False
+
+        def apply(self, x, y, sign):
+            y.copy_(x * sign)
+
+        def close(self):
+            self.closed = True
+
+    class FakeSharded:
+        def __init__(self, n):
+            self.plan, self.calls = FakePlan(n), 0
+
+        def apply(self, x, y, sign):
+            self.calls += 1
+            y.copy_(2 * x * sign)
+            return y
+
+    class Spec(parallel.ShardSpec):
+        def __init__(self, min_dim):
+            self.rank, self.world, self.dist, self.mode, self.min_dim = 0, 2, None, "ket", min_dim
+            self.made, self.agreed = [], 0
+
+        def heff(self, ctx, M, W, F, site, oneSite):
+            sh = FakeSharded(M[site].numel() * M[site + 1].shape[0] * M[site + 1].shape[2] // M[site].shape[2])
+            self.made.append(sh)
+            return sh
+
+        def consensus(self, t):
+            self.agreed += 1
+            return t
+
+    class Ctx:
+        code, device, tdtype, npdtype = 1, torch.device("cpu"), torch.complex128, np.complex128
+
+        def dev(self, a):
+            return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, dtype=np.complex128))
+
+    seen = {}
+
+    def fake_davidson(matvec, x0, n, code, device, nroots=1, plan=None, native=None, consensus=None, **kw):
+        y = torch.empty_like(x0[0])
+        matvec(x0[0], y)
+        seen.update(plan=plan, native=native, consensus=consensus)
+        if consensus is not None:
+            consensus(y)
+        return np.array([-1.0 + 0j]), [x0[0] / x0[0].norm()]
+
+    def fake_make_plan(M, W, F, site, oneSite, ctx, block_masks=None):
+        d1, Dl, _ = M[site].shape
+        d2, _, Dr = M[site + 1].shape
+        return FakePlan(d1 * d2 * Dl * Dr), (d1, d2, Dl, Dr)
+
+    monkeypatch.setattr(eigs, "davidson", fake_davidson)
+    monkeypatch.setattr(eigs, "make_plan", fake_make_plan)
+    monkeypatch.setattr(eigs, "two_site_guess", lambda A, B, ctx: torch.einsum("ijk,lkm->iljm", A, B).contiguous())
+    monkeypatch.setattr(eigs, "check_overlap", lambda guess, vecs, E, preserveState, ctx: (np.atleast_1d(E), vecs, 1.0))
+    rng = np.random.default_rng(0)
+    mk = lambda *s: torch.from_numpy(rng.standard_normal(s) + 0j)
+    mps = [[mk(2, 4, 8), mk(2, 8, 8), mk(2, 8, 8), mk(2, 8, 4)]]
+    ctx = Ctx()
+    spec = Spec(min_dim=8)
+    E, V, _ = eigs.calc_eigs(mps, [[None] * 4], [[None] * 5], 1, 1, oneSite=False, ctx=ctx, shard=spec, return_device=True)
+    assert len(spec.made) == 1 and spec.made[0].calls == 1 and spec.made[0].plan.closed     # Dl = Dr = 8: sharded
+    assert seen["plan"] is None and seen["native"] is False and seen["consensus"] is not None
+    assert spec.agreed == 2                                                                  # control scalars + the eigenvector
+    assert E == 1.0 and tuple(V.shape) == (2 * 2 * 8 * 8, 1)
+    E, V, _ = eigs.calc_eigs(mps, [[None] * 4], [[None] * 5], 0, 1, oneSite=False, ctx=ctx, shard=spec, return_device=True)
+    assert len(spec.made) == 1 and seen["consensus"] is None and seen["plan"] is not None   # Dl = 4 < min_dim: local plan
+
+
+def test_shard_spec_keeps_every_rank_a_ket_range():
+    from pydmrg_b200.parallel import ShardSpec, ket_chunks
+    s = ShardSpec(3, 8, None, min_dim=64)
+    assert s.min_dim == 128 and all(n > 0 for _, n in ket_chunks(s.min_dim, 8))
