@@ -1,0 +1,42 @@
+#!/bin/bash
+# First GPU session of the next round: everything that was written after the round-1 GPU budget was spent,
+# in the order of what it unblocks.  Each item is one gpurun call (run from the repo root, here):
+#
+#   1 GPU :  gpurun --timeout 1500 -- 'bash tools/round2_validate.sh one'
+#   2 GPUs:  gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_validate.sh two'
+#   8 GPUs:  gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_validate.sh eight'
+#
+# Outputs land in gpurun_out/ (merged back); copy what should be judged into profiles/.
+set -u
+mkdir -p gpurun_out
+case "${1:-one}" in
+one)
+  # (a) the validated suite + the pending tests (two-site nStates=2, state-averaged truncation)
+  timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>&1; echo "gpu tests rc=$?" | tee -a gpurun_out/r2_gpu_tests.log
+  PDMRG_RUN_PENDING=1 timeout 300 python -m pytest tests/test_pending_gpu.py -m gpu -q > gpurun_out/r2_pending.log 2>&1; echo "pending rc=$?" | tee -a gpurun_out/r2_pending.log
+  # (b) bench line with the start policy of the warm-started truncation in place (profiles/README note)
+  timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_err.log; echo "bench rc=$?"
+  # (c) where does a latency-bound Davidson cycle go (host vs device), one process
+  timeout 200 python tools/scan_contention.py > gpurun_out/r2_contention_n1.txt 2>&1
+  ;;
+two)
+  # sharded sweeps (run_dmrg(shard=...)) against unsharded ones, then the chi=1024 sweep timing
+  timeout 400 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
+      tests/mgpu_sharded_sweep_check.py > gpurun_out/r2_sharded_sweep_n2.txt 2>&1; echo "sharded sweep check rc=$?"
+  PDMRG_CHECK_TIMING=1 timeout 400 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 \
+      tests/mgpu_sharded_sweep_check.py > gpurun_out/r2_sharded_sweep_timing_n2.txt 2>&1; echo "timing rc=$?"
+  ;;
+eight)
+  # host contention of the latency-bound scan: cycles/s per rank with 1, 2, 4, 8 ranks, unpinned and pinned
+  for n in 1 2 4 8; do
+    for pin in "" "--pin"; do
+      timeout 200 python -m torch.distributed.run --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n \
+          tools/scan_contention.py $pin > gpurun_out/r2_contention_n${n}${pin:+_pin}.txt 2>&1
+    done
+  done
+  nproc > gpurun_out/r2_host.txt; lscpu >> gpurun_out/r2_host.txt 2>&1; cat /sys/fs/cgroup/cpu.max >> gpurun_out/r2_host.txt 2>&1
+  nvidia-smi topo -m >> gpurun_out/r2_host.txt 2>&1
+  timeout 300 python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29630 \
+      -m pydmrg_b200.scan --N 50 --chi 256 --points 64 --max-iter 3 --pin-cores > gpurun_out/r2_scan_n8_pinned.json 2> gpurun_out/r2_scan_err.log
+  ;;
+esac
