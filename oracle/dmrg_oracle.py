@@ -468,19 +468,41 @@ def onesite_step(mps, mpo, env, site, direction, alg="davidson", mode="blas", st
     return E[0], EE, EEs
 
 
+def increase_mbd(mps, mbd, d=2):
+    """Zero-pad a state to the bond profile of a larger chi.  tools/mps_tools.py:244-279 (open chain)."""
+    N = len(mps)
+    out = []
+    for site, M in enumerate(mps):
+        if site < N // 2:                                                # :248-252
+            sz1, sz2 = min(d ** site, mbd), min(d ** (site + 1), mbd)
+        elif N % 2 == 1 and site == N // 2:                              # :253-258
+            sz1 = sz2 = min(d ** site, mbd)
+        else:                                                            # :259-264
+            sz1, sz2 = min(d ** (N - site), mbd), min(d ** (N - site - 1), mbd)
+        _, ny, nz = M.shape
+        out.append(np.pad(M.astype(np.complex128), ((0, 0), (0, sz1 - ny), (0, sz2 - nz))))
+    return out
+
+
 def run_dmrg_onesite(mpo, mbd, tol=1e-5, max_iter=10, min_iter=0, alg="davidson",
-                     gauge_site_save=None, mps=None, mode="blas", stats=None):
+                     gauge_site_save=None, mps=None, mode="blas", stats=None, gauge_site_load=0):
     """run_dmrg for a single chi, nStates=1, fresh random start.  dmrg.py:309-508 with
     run_sweeps :238-307, rightSweep/leftSweep :150-208, checkConv :210-223.
-    Call np.random.seed(k) first to reproduce the reference's initial MPS."""
+    Call np.random.seed(k) first to reproduce the reference's initial MPS.  ``mps`` + ``gauge_site_load``: continue
+    from a saved state whose centre sits on that site (dmrg.py:352-358, 391, run_sweeps :248-259)."""
     N = len(mpo[0])
     if gauge_site_save is None:
         gauge_site_save = N // 2 + 1
     if mps is None:
         mps = make_mps_right(random_mps(N, mbd))
-    env = build_env(mps, mpo, mbd, gauge_site=0, mode=mode)
+    env = build_env(mps, mpo, mbd, gauge_site=gauge_site_load, mode=mode)
     it, E_prev, cont = 0, 0, True
     E = EE = EEs = None
+    if gauge_site_load != 0:                                             # dmrg.py:248-259 (a loaded state)
+        for site in range(gauge_site_load, N - 1):
+            onesite_step(mps, mpo, env, site, "right", alg, mode, stats)
+        for site in range(N - 1, 0, -1):
+            onesite_step(mps, mpo, env, site, "left", alg, mode, stats)
     while cont:
         for site in range(0, N - 1):
             e, ee, ees = onesite_step(mps, mpo, env, site, "right", alg, mode, stats)

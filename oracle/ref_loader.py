@@ -9,8 +9,9 @@ installing four in-memory shims first:
    pydmrg/tools/la_tools.py:12 star-imports.  It only re-exports NumPy primitives
    (call sites la_tools.py:20,28-30,451,459-464,591-601,638-639); the Davidson arithmetic
    itself (``davidson_nosym1``, la_tools.py:402-557) lives in the reference.
-3. ``h5py`` -- imported at pydmrg/tools/mps_tools.py:6; an empty module is enough as
-   long as ``fname=None``.
+3. ``h5py`` -- imported at pydmrg/tools/mps_tools.py:6; when it is not installed a mini-shim
+   (File / create_group / create_dataset / get over one .npz archive) stands in, enough for the
+   file-based flows of the reference (``fname=...``, ``calcLeftState=True``).
 4. ``pyscf.lib`` for pydmrg/idmrg.py:3-4 with ``eig = tools.la_tools.eig`` (la_tools is
    the reference's adapted copy of that routine) and ``einsum = np.einsum``.
 
@@ -62,7 +63,47 @@ def _install_shims():
         try:
             import h5py  # noqa: F401
         except Exception:
-            sys.modules["h5py"] = types.ModuleType("h5py")
+            sys.modules["h5py"] = _h5py_shim()
+
+
+def _h5py_shim():
+    """The few h5py calls of pydmrg/tools/mps_tools.py:320-373 (File as a context manager, create_group,
+    create_dataset(name, data=...), get(path)) over one .npz archive written at the same path -- enough for the
+    reference's file-based flows (run_dmrg(fname=...), calcLeftState, chi schedules) where h5py is not installed."""
+    mod = types.ModuleType("h5py")
+
+    class _Group:
+        def __init__(self, store, prefix):
+            self._store, self._prefix = store, prefix
+
+        def create_group(self, name):
+            return _Group(self._store, self._prefix + name + "/")
+
+        def create_dataset(self, name, data=None, **kw):
+            self._store[self._prefix + name] = np.asarray(data)
+
+    class File(_Group):
+        def __init__(self, path, mode="r"):
+            _Group.__init__(self, {}, "")
+            self._path, self._mode = path, mode
+            if mode == "r":
+                with np.load(path) as z:
+                    self._store = {k.replace("|", "/"): z[k] for k in z.files}
+
+        def get(self, key):
+            return self._store.get(key)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            if self._mode != "r":
+                with open(self._path, "wb") as fh:
+                    np.savez(fh, **{k.replace("/", "|"): v for k, v in self._store.items()})
+            return False
+
+    mod.File = File
+    return mod
 
 
 _REF = None

@@ -33,4 +33,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {k: np.load(os.path.join(d, k + ".npz")) for k in ("kernels", "davidson", "runs", "multistate")}
+    return {k: np.load(os.path.join(d, k + ".npz")) for k in ("kernels", "davidson", "runs", "multistate", "leftright")}

@@ -195,11 +195,62 @@ def multistate_fixture():
             print(k, out[k])
 
 
+def leftright_fixture():
+    """Reference run_dmrg(calcLeftState=True) (dmrg.py:338, 448-488: second DMRG on mpo_conj_trans(mpo); needs
+    fname, i.e. the HDF5 round trip -- served by the h5py mini-shim of oracle/ref_loader.py where h5py is absent),
+    observables <l|O|r>/<l|r> through tools/contract.py:5-44 as the scan scripts compute them
+    (scripts/asep/current/multipleStates.py:89-101), and a chi schedule continued through saved states."""
+    import tempfile
+    out = {}
+    cases = (("tasep8", 8, (0.35, 0., 1., 0., 2. / 3., 0., -0.5), 9), ("asep8", 8, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5), 10))
+    for tag, N, prm, seed in cases:
+        mpo = ref.asep.return_mpo(N, prm)
+        cmpo = ref.asep.curr_mpo(N, prm)
+        tmp = tempfile.mkdtemp()
+        np.random.seed(seed)
+        with quiet():
+            r = ref.dmrg.run_dmrg(mpo, mbd=16, tol=1e-10, maxIter=6, fname=os.path.join(tmp, "st"), calcLeftState=True,
+                                  returnState=True, returnEntSpec=True)
+            # The two lists returned in memory are ONE aliased object (dmrg.py:371 passes mpsList itself to
+            # make_all_mps_right, so the left run overwrites the right state); the files written after each run
+            # hold the two states, and they are what the scan scripts contract.
+            assert r[4][0] is r[4][1]
+            mps, _ = ref.mps_tools.load_mps(os.path.join(tmp, "st_mbd0"))
+            mpsl, _ = ref.mps_tools.load_mps(os.path.join(tmp, "st_mbd0_left"))
+            num = ref.contract.full_contract(mps=mps, mpo=cmpo, lmps=mpsl)
+            den = ref.contract.full_contract(mps=mps, lmps=mpsl)
+            hnum = ref.contract.full_contract(mps=mps, mpo=mpo, lmps=mpsl)
+        u, _ = ref.ed.ed(mpo)
+        out[tag + "_E"], out[tag + "_EE"], out[tag + "_EEl"] = np.array(r[0]), np.array(r[1][0]), np.array(r[1][1])
+        out[tag + "_EEs"], out[tag + "_EEsl"] = r[3][0], r[3][1]
+        out[tag + "_current_lr"], out[tag + "_energy_lr"] = np.array(num / den), np.array(hnum / den)
+        out[tag + "_ed_top"] = np.array(u[0])
+        out[tag + "_params"] = np.array(prm)
+        out[tag + "_cfg"] = np.array([N, 16, seed])
+    # chi schedule [4, 8, 16] continued through the saved states (dmrg.py:352-358, mps_tools.py:244-279)
+    prm = cases[1][2]
+    mpo = ref.asep.return_mpo(8, prm)
+    tmp = tempfile.mkdtemp()
+    np.random.seed(11)
+    with quiet():
+        r = ref.dmrg.run_dmrg(mpo, mbd=[4, 8, 16], tol=1e-10, maxIter=4, fname=os.path.join(tmp, "st"))
+    out["sched_E"], out["sched_EE"] = np.array(r[0]), np.array(r[1])
+    out["sched_cfg"] = np.array([8, 11])
+    np.savez_compressed(os.path.join(HERE, "leftright.npz"), **out)
+    for k in sorted(out):
+        if out[k].size <= 3:
+            print(k, out[k])
+
+
 if __name__ == "__main__":
-    if "multistate" in sys.argv[1:]:
-        multistate_fixture()
+    if "multistate" in sys.argv[1:] or "leftright" in sys.argv[1:]:
+        if "multistate" in sys.argv[1:]:
+            multistate_fixture()
+        if "leftright" in sys.argv[1:]:
+            leftright_fixture()
         sys.exit(0)
     kernels_fixture()
     davidson_fixture()
     runs_fixture()
     multistate_fixture()
+    leftright_fixture()

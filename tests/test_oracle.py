@@ -261,3 +261,61 @@ def test_twosite_state_averaged_truncation_properties():
             proj = iso @ iso.conj().T @ m if direction == "right" else m @ iso @ iso.conj().T
             assert np.allclose(Am @ Bm, proj, atol=1e-13)
         assert As[0] is As[1] if direction == "right" else Bs[0] is Bs[1]
+
+
+# ---------------------------------------------------------------------------------------
+# left + right eigenstates and observables <l|O|r>/<l|r> (BASELINE configs[2]); chi schedules through saved states
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["tasep8", "asep8"])
+def test_left_and_right_eigenstates_match_reference_run(golden, tag):
+    """The reference's run_dmrg(calcLeftState=True) -- a second DMRG on mpo_conj_trans(mpo), dmrg.py:338,448-488 --
+    against the oracle's two runs: eigenvalue, both entropies, and the current / energy <l|O|r>/<l|r>
+    (tools/contract.py:5-44) that the scan scripts report.  The reference's left run starts from its converged
+    right state (aliased lists, dmrg.py:371), the oracle's from the seeded start; converged quantities agree to
+    the reference's solver floor (||r|| <= 1e-7)."""
+    from pydmrg_b200.mpo import mpo_conj_trans
+    g = golden["leftright"]
+    N, mbd, seed = (int(v) for v in g[tag + "_cfg"])
+    prm = g[tag + "_params"]
+    mpo = _asep_mpo(N, prm)
+    np.random.seed(seed)
+    E, EE, EEs, mps_r, _ = orc.run_dmrg_onesite(mpo, mbd, tol=1e-10, max_iter=6)
+    np.random.seed(seed)
+    El, EEl, EEsl, mps_l, _ = orc.run_dmrg_onesite(mpo_conj_trans(mpo), mbd, tol=1e-10, max_iter=6)
+    scale = abs(g[tag + "_E"])
+    assert abs(E - g[tag + "_E"]) < 1e-7 * scale and abs(E - g[tag + "_ed_top"]) < 1e-7 * scale
+    assert abs(El - np.conj(E)) < 1e-7 * scale
+    assert abs(EE - g[tag + "_EE"]) < 1e-6 and abs(EEl - g[tag + "_EEl"]) < 1e-6
+    den = orc.full_contract(None, mps_r, mps_l)
+    cur = orc.full_contract(_asep_curr_mpo(N, prm), mps_r, mps_l) / den
+    ene = orc.full_contract(mpo, mps_r, mps_l) / den
+    assert abs(cur - g[tag + "_current_lr"]) < 1e-6 * max(1.0, abs(g[tag + "_current_lr"]))
+    assert abs(ene - g[tag + "_energy_lr"]) < 1e-7 * scale and abs(ene - g[tag + "_ed_top"]) < 1e-7 * scale
+
+
+def test_chi_schedule_through_saved_states(golden):
+    """run_dmrg(mbd=[4, 8, 16], fname=...): every stage loads the previous state (centre on gaugeSiteSave),
+    zero-pads it (mps_tools.py:244-279) and sweeps from the loaded gauge site (dmrg.py:352-358, 248-259)."""
+    g = golden["leftright"]
+    N, seed = (int(v) for v in g["sched_cfg"])
+    mpo = _asep_mpo(N, g["asep8_params"])
+    np.random.seed(seed)
+    mps, gs = None, 0
+    for i, chi in enumerate((4, 8, 16)):
+        if mps is not None:
+            mps = orc.increase_mbd(mps, chi)
+        E, EE, EEs, mps, _ = orc.run_dmrg_onesite(mpo, chi, tol=1e-10, max_iter=4, mps=mps, gauge_site_load=gs)
+        gs = N // 2 + 1
+        assert abs(E - g["sched_E"][i]) < 2e-7 * abs(g["sched_E"][i])
+        assert abs(EE - g["sched_EE"][i]) < 1e-5
+
+
+def test_increase_mbd_equals_product_builder():
+    from pydmrg_b200 import mps as mps_tools
+    for N in (7, 8):
+        np.random.seed(N)
+        a = orc.random_mps(N, 4)
+        b = [t.copy() for t in a]
+        pa = orc.increase_mbd(a, 16)
+        pb = mps_tools.increase_mbd(b, 16)
+        assert all(x.shape == y.shape and np.array_equal(x, y) for x, y in zip(pa, pb))

@@ -64,3 +64,25 @@ def test_state_averaged_twosite_truncation(P, direction, dtype):
         assert np.max(np.abs(iso.conj().T @ iso - np.eye(k))) < 1e-12
         assert np.max(np.abs(Am @ Bm - Amo @ Bmo)) < 1e-10
     assert abs(EE - EEo) < 1e-10 and np.max(np.abs(Sn - Sno)) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["tasep8", "asep8"])
+def test_left_right_run_matches_reference_fixture(P, tag):
+    """run_dmrg(calcLeftState=True) against tests/golden/leftright.npz (the unmodified reference's run; states read
+    back from its saved files): E, both entropies, current and energy <l|O|r>/<l|r> (north-star: 1e-8 observables on
+    converged states; the reference itself stops at ||r|| <= 1e-7, hence 1e-6 against its numbers and 1e-8 against ED)."""
+    g = np.load(os.path.join(GOLD, "leftright.npz"))
+    N, mbd, seed = (int(v) for v in g[tag + "_cfg"])
+    prm = tuple(float(v) for v in g[tag + "_params"])
+    mpo = P.mpo.asep_mpo(N, prm)
+    np.random.seed(seed)
+    E, EE, gap, mps = P.dmrg.run_dmrg(mpo, mbd=mbd, tol=1e-12, maxIter=6, res_tol=1e-11, calcLeftState=True, returnState=True)
+    r, l = mps
+    scale = abs(g[tag + "_ed_top"])
+    assert abs(E - g[tag + "_ed_top"]) < 1e-9 * scale and abs(E - g[tag + "_E"]) < 1e-7 * scale
+    assert abs(EE[0] - g[tag + "_EE"]) < 1e-6 and abs(EE[1] - g[tag + "_EEl"]) < 1e-6
+    den = P.contract.full_contract(mps=r, lmps=l)
+    cur = P.contract.full_contract(mpo=P.mpo.asep_curr_mpo(N, prm), mps=r, lmps=l) / den
+    ene = P.contract.full_contract(mpo=mpo, mps=r, lmps=l) / den
+    assert abs(cur - g[tag + "_current_lr"]) < 1e-6 * max(1.0, abs(g[tag + "_current_lr"]))
+    assert abs(ene - g[tag + "_ed_top"]) < 1e-8 * scale
