@@ -174,6 +174,17 @@ int pdmrg_env_update_right(int dtype, int d, int Dl, int Dr, int wl, int wr, con
 int pdmrg_env_update_left(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
                           const void* R, const void* B, const void* Bbra, void* out,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Column-restricted variants for sharded sweeps (same contractions, tools/env_tools.py:40-50 /
+ * 28-38): only the entries of the new block whose KET index (last index of `out`) lies in [k0, k0+kn) are computed
+ * and stored, in place, into the full-size `out` (D_bra, w, D_ket); everything else in `out` is left untouched.
+ * Ranks owning disjoint ket ranges build the whole block with one exchange.  Workspace: pdmrg_env_workspace_bytes.
+ * k0 should be a multiple of 2 for f64 (16-byte aligned stores). */
+int pdmrg_env_update_right_cols(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                                const void* L, const void* A, const void* Abra, int k0, int kn, void* out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int pdmrg_env_update_left_cols(int dtype, int d, int Dl, int Dr, int wl, int wr, const void* W_host,
+                               const void* R, const void* B, const void* Bbra, int k0, int kn, void* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Krylov vector kernels for the Davidson loop (tools/la_tools.py:449-457, 469-470,
  *      479-482, 524-536).  Vectors have n elements; a "basis" is m vectors at X + i*stride. */

@@ -63,6 +63,8 @@ def _load():
         "pdmrg_env_workspace_bytes": (sz, [i, i, i, i, i, i]),
         "pdmrg_env_update_right": (i, [i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
         "pdmrg_env_update_left": (i, [i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "pdmrg_env_update_right_cols": (i, [i, i, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, sz, vp]),
+        "pdmrg_env_update_left_cols": (i, [i, i, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, sz, vp]),
         "pdmrg_vec_dots": (i, [i, ll, i, vp, ll, vp, vp, vp, sz, vp]),
         "pdmrg_vec_combine": (i, [i, ll, i, vp, vp, ll, vp, i, vp]),
         "pdmrg_davidson_residual": (i, [i, ll, i, vp, vp, vp, vp, ll, vp, vp, vp, sz, vp]),

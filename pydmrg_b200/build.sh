@@ -4,4 +4,4 @@ set -e
 cd "$(dirname "$0")/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
      -I/usr/local/cuda/include ${PDMRG_NVCC_FLAGS} \
-     -o ../libpydmrg_b200.so api.cu gemm_nt.cu tensor_ops.cu heff.cu krylov.cu solver.cu comm.cu davidson.cu -ldl
+     -o ../libpydmrg_b200.so api.cu gemm_nt.cu tensor_ops.cu heff.cu krylov.cu solver.cu comm.cu davidson.cu env_cols.cu -ldl

@@ -237,6 +237,32 @@ def env_update_left(B, W, R, Bbra, workspace):
     return out
 
 
+def env_update_cols(direction, T, W, blk, Tbra, k0, kn, workspace, out=None):
+    """The slice of a block update owned by one rank of a sharded sweep (csrc/env_cols.cu): the entries of the new
+    block whose ket index lies in [k0, k0+kn), written in place into the full-size ``out`` (zero-initialised when
+    not given).  ``direction`` 'right': new left block from ``blk`` = L and T = A; 'left': new right block from
+    ``blk`` = R and T = B."""
+    code = dtype_code(T)
+    d, Dl, Dr = T.shape
+    Wh, Wp = _w_host(W, code)
+    if direction == "right":
+        wl = blk.shape[1]
+        wr = wl if W is None else W.shape[1]
+        shape, fn, name = (Dr, wr, Dr), lib.pdmrg_env_update_right_cols, "pdmrg_env_update_right_cols"
+    else:
+        wr = blk.shape[1]
+        wl = wr if W is None else W.shape[0]
+        shape, fn, name = (Dl, wl, Dl), lib.pdmrg_env_update_left_cols, "pdmrg_env_update_left_cols"
+    if out is None:
+        out = torch.zeros(shape, dtype=T.dtype, device=T.device)
+    assert tuple(out.shape) == shape and out.is_contiguous()
+    nb = lib.pdmrg_env_workspace_bytes(code, d, Dl, Dr, wl, wr)
+    ws = workspace.get(nb)
+    check(fn(code, d, Dl, Dr, wl, wr, Wp, _ptr(blk), _ptr(T), _ptr(Tbra), int(k0), int(kn), _ptr(out), _ptr(ws), ws.numel(),
+             _stream()), name)
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 class VecOps:
     """Krylov vector kernels bound to one dtype / vector length / scratch buffer."""

@@ -162,14 +162,25 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
         tick.lap(stats, "t_svd")
         mpsL[0][site] = like(A, proto)
         mpsL[0][site + 1] = like(B, proto)
+    shard = solver.get("shard")
     if direction == "right":
+        split = shard is not None and shard.wants_env(A.shape[1], A.shape[2])
         for m in range(len(W)):
-            out = D.env_update_right(A, W[m][site], ctx.dev(F[m][site]), None, ctx.ws)
+            if split:
+                out = shard.env_update("right", A, W[m][site], ctx.dev(F[m][site]), ctx)
+            else:
+                out = D.env_update_right(A, W[m][site], ctx.dev(F[m][site]), None, ctx.ws)
             F[m][site + 1] = like(out, proto)
     else:
+        split = shard is not None and shard.wants_env(B.shape[1], B.shape[2])
         for m in range(len(W)):
-            out = D.env_update_left(B, W[m][site + 1], ctx.dev(F[m][site + 2]), None, ctx.ws)
+            if split:
+                out = shard.env_update("left", B, W[m][site + 1], ctx.dev(F[m][site + 2]), ctx)
+            else:
+                out = D.env_update_left(B, W[m][site + 1], ctx.dev(F[m][site + 2]), None, ctx.ws)
             F[m][site + 1] = like(out, proto)
+    if split and stats is not None:
+        stats["n_sharded_env"] = stats.get("n_sharded_env", 0) + 1
     tick.lap(stats, "t_env")
     return E, mpsL, F, EE, EEs, S
 

@@ -276,16 +276,33 @@ class ShardSpec:
     """How a sweep shards its mat-vecs (passed as ``run_dmrg(..., shard=ShardSpec(rank, world, dist))``):
     every rank runs the whole sweep on replicated tensors; the local eigenproblems of bonds with
     min(Dl, Dr) >= ``min_dim`` use a ShardedHeff in ``mode`` ('ket': balanced for any MPO; 'bond': blocks of
-    the MPO bond) -- one NCCL all-reduce of y per mat-vec.  Truncation and block updates stay replicated."""
+    the MPO bond) -- one NCCL all-reduce of y per mat-vec; with ``shard_env`` the block updates of those bonds
+    are split over the ket index of the new block (one all-reduce of the block).  The truncation stays replicated."""
 
-    def __init__(self, rank, world, dist, mode="ket", min_dim=256):
+    def __init__(self, rank, world, dist, mode="ket", min_dim=256, shard_env=True):
         self.rank, self.world, self.dist, self.mode = int(rank), int(world), dist, mode
         self.min_dim = max(int(min_dim), 16 * self.world)       # every rank must own a TMA-aligned ket range
+        self.shard_env = bool(shard_env)
 
     def heff(self, ctx, M, W, F, site, oneSite):
         from .eigs import _site_ops
         ops, P, shape = _site_ops(M, W, F, site, oneSite, ctx)
         return ShardedHeff(ctx.code, P, shape[-2], shape[-1], ops, ctx.ws, self.rank, self.world, self.dist, mode=self.mode)
+
+    def env_update(self, direction, T, W, blk, ctx):
+        """Block update split over the ket index of the NEW block: every rank computes the columns
+        it owns (1/world of both GEMM stages, csrc/env_cols.cu) into a zero-initialised full-size block; one
+        all-reduce assembles it on every rank."""
+        import torch
+        from . import device as D
+        n = T.shape[2] if direction == "right" else T.shape[1]
+        k0, kn = ket_chunks(n, self.world)[self.rank]
+        out = D.env_update_cols(direction, T, W, blk, None, k0, kn, ctx.ws)
+        self.dist.all_reduce(torch.view_as_real(out) if out.is_complex() else out, op=self.dist.ReduceOp.SUM)
+        return out
+
+    def wants_env(self, *dims):
+        return self.world > 1 and self.shard_env and min(dims) >= self.min_dim
 
     def consensus(self, t):
         """Overwrite a small device tensor by rank 0's copy (control scalars, eigenvectors)."""

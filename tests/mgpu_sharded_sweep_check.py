@@ -36,17 +36,18 @@ def main():
             st = {}
             out = dmrg.run_dmrg(mpo, mbd=chi, tol=0.0, maxIter=3, twoSite=True, dtype=dtype, stats=st, res_tol=1e-11,
                                 returnEntSpec=True, shard=spec)
-            res[mode] = (complex(out[0]), float(np.real(out[1])), st.get("n_sharded_solves", 0), st.get("n_matvec", 0))
+            res[mode] = (complex(out[0]), float(np.real(out[1])), st.get("n_sharded_solves", 0), st.get("n_matvec", 0),
+                         st.get("n_sharded_env", 0))
         E0, EE0 = res[None][0], res[None][1]
         for mode in ("ket", "bond"):
-            E, EE, ns, nmv = res[mode]
+            E, EE, ns, nmv, nenv = res[mode]
             # every rank must hold the same numbers as rank 0
             t = torch.tensor([E.real, E.imag, EE], dtype=torch.float64, device="cuda")
             t0 = t.clone(); dist.broadcast(t0, 0)
             same = bool(torch.equal(t, t0))
-            good = abs(E - E0) < 1e-10 * abs(E0) and abs(EE - EE0) < 1e-8 and ns > 0 and same
+            good = abs(E - E0) < 1e-10 * abs(E0) and abs(EE - EE0) < 1e-8 and ns > 0 and nenv > 0 and same
             ok = ok and good
-            report["%s_%s" % (model, mode)] = {"dE": abs(E - E0), "dEE": abs(EE - EE0), "sharded_solves": ns,
+            report["%s_%s" % (model, mode)] = {"dE": abs(E - E0), "dEE": abs(EE - EE0), "sharded_solves": ns, "sharded_block_updates": nenv,
                                                "n_matvec": nmv, "n_matvec_unsharded": res[None][3], "same_on_all_ranks": same}
     if os.environ.get("PDMRG_CHECK_TIMING") == "1":
         # device-resident state as in bench.py full_sweep: ramp, then sweeps at chi; the last one is a converged sweep
@@ -68,7 +69,8 @@ def main():
                 E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, big, ctx=ctx, stats=st, recycle=cache, shard=spec)
                 torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
             report["sweep_sec_%s" % (mode or "unsharded")] = {"sec": ts, "n_matvec": st.get("n_matvec"), "E": [E.real, E.imag],
-                                                             "sharded_solves": st.get("n_sharded_solves", 0)}
+                                                             "sharded_solves": st.get("n_sharded_solves", 0),
+                                                             "sharded_block_updates": st.get("n_sharded_env", 0)}
             del mpsL, F, cache
             torch.cuda.empty_cache()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -86,3 +86,29 @@ def test_left_right_run_matches_reference_fixture(P, tag):
     ene = P.contract.full_contract(mpo=mpo, mps=r, lmps=l) / den
     assert abs(cur - g[tag + "_current_lr"]) < 1e-6 * max(1.0, abs(g[tag + "_current_lr"]))
     assert abs(ene - g[tag + "_ed_top"]) < 1e-8 * scale
+
+
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+@pytest.mark.parametrize("dims", [(2, 96, 80), (2, 64, 64), (2, 40, 200)])
+def test_column_restricted_block_updates(P, dtype, dims):
+    """pdmrg_env_update_right_cols / _left_cols (csrc/env_cols.cu): the ket-column slices computed separately add
+    up to the unrestricted update (validated entry points) and leave every other entry of the output untouched."""
+    import torch
+    from pydmrg_b200 import device as D
+    c = P.core.Context(dtype)
+    rng = np.random.default_rng(21)
+    d, Dl, Dr = dims
+    rnd = (lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)) if dtype == "c128" else (lambda *s: rng.standard_normal(s))
+    W = P.mpo.asep_mpo(6, PRM)[0][2].astype(np.complex128 if dtype == "c128" else np.float64)
+    w = W.shape[0]
+    A = c.dev(rnd(d, Dl, Dr))
+    for direction, blk, n in (("right", c.dev(rnd(Dl, w, Dl)), Dr), ("left", c.dev(rnd(Dr, w, Dr)), Dl)):
+        full = (D.env_update_right if direction == "right" else D.env_update_left)(A, W, blk, None, c.ws)
+        out = torch.full_like(full, float("nan"))
+        cuts = [0, 16, 16, min(48, n - 8), n]                 # one empty range
+        for k0, k1 in zip(cuts[:-1], cuts[1:]):
+            D.env_update_cols(direction, A, W, blk, None, k0, k1 - k0, c.ws, out=out)
+        torch.cuda.synchronize()
+        assert not bool(torch.isnan(torch.view_as_real(out) if out.is_complex() else out).any())
+        err = (out - full).abs().max().item() / full.abs().max().item()
+        assert err < 1e-13, (direction, err)
