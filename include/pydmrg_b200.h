@@ -198,7 +198,7 @@ int pdmrg_vec_combine(int dtype, long long n, int m, const void* coef_host, cons
 int pdmrg_davidson_residual(int dtype, long long n, int m, const void* v_host, const void* e_host,
                             const void* XS, const void* AX, long long stride, void* r,
                             double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream);
-/* r = (r * scale_dev[0]^-1/2 if scale_dev) - sum_i c_dev[i] X_i ; norm2_dev[0] = ||r||^2.
+/* r = (r - sum_i c_dev[i] X_i) * (scale_dev ? scale_dev[0]^-1/2 : 1) ; norm2_dev[0] = ||r||^2 of the result.
  * Coefficients stay on the device so that dots -> project needs no host round trip. */
 int pdmrg_vec_project(int dtype, long long n, int m, const void* X, long long stride,
                       const void* c_dev, const double* scale_dev, void* r,

@@ -140,11 +140,14 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
         else:
             guesses.append(two_site_guess(ctx.dev(mpsL[s][site]), ctx.dev(mpsL[s][site + 1]), ctx).reshape(-1))
     if alg == "davidson" and sharded is not None:
+        # identical start vectors on every rank: together with the all-reduced images and the deterministic vector
+        # kernels this keeps the ranks' Krylov bases identical (a residual of norm 1e-9 that differed by 1e-13
+        # between ranks would otherwise become a 1e-4 relative inconsistency of the next, normalised, direction)
+        for gk in guesses:
+            shard.consensus(gk)
         vals, vecs = davidson(lambda x, y: sharded.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=None,
                               native=False, max_cycle=max_cycle, consensus=shard.consensus)
-        for vk in vecs:
-            shard.consensus(vk)
         E = -vals
         if stats is not None:
             stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
@@ -159,6 +162,13 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
         E, vecs = _eigs_arnoldi(plan, n, nS, guesses[0], ctx)
     else:
         raise ValueError("alg must be 'davidson', 'exact' or 'arnoldi'")
+    if shard is not None and shard.world > 1:
+        # EVERY solve of a sharded run -- also the small bonds every rank solves on its own -- ends with rank 0's
+        # eigenpairs on all ranks: a rounding difference that flips one convergence test would otherwise leave the
+        # ranks with states that differ at the solver tolerance, and the next sharded mat-vec would mix blocks
+        # built from different bases.  E steers checkConv, i.e. the number of sweeps (= collectives): same on all.
+        vecs = [shard.consensus(vk.contiguous()) for vk in vecs]
+        E = shard.consensus_host(np.asarray(E, dtype=np.complex128), ctx)
     if not isinstance(orthonormalize, bool):                    # diag_tools.py:275-283
         orthonormalize = (nS > 1) and (abs(E[0] - E[1]) < orthonormalize)
     if nS > 1 and orthonormalize:

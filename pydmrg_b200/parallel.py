@@ -301,6 +301,16 @@ class ShardSpec:
         self.dist.all_reduce(torch.view_as_real(out) if out.is_complex() else out, op=self.dist.ReduceOp.SUM)
         return out
 
+    def consensus_host(self, a, ctx):
+        """Rank 0's copy of a small host array (eigenvalues) on every rank."""
+        import torch
+        if self.world <= 1:
+            return a
+        a = np.ascontiguousarray(a, dtype=np.complex128)
+        t = torch.view_as_real(torch.from_numpy(a.reshape(-1).copy())).to(ctx.device)
+        self.dist.broadcast(t, src=0)
+        return torch.view_as_complex(t.cpu().contiguous()).numpy().reshape(a.shape)
+
     def wants_env(self, *dims):
         return self.world > 1 and self.shard_env and min(dims) >= self.min_dim
 

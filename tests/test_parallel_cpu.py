@@ -204,6 +204,10 @@ def test_calc_eigs_routes_large_bonds_through_the_sharded_matvec(monkeypatch):
             self.agreed += 1
             return t
 
+        def consensus_host(self, a, ctx):
+            self.host_agreed = getattr(self, "host_agreed", 0) + 1
+            return a
+
     class Ctx:
         code, device, tdtype, npdtype = 1, torch.device("cpu"), torch.complex128, np.complex128
 
@@ -237,10 +241,11 @@ def test_calc_eigs_routes_large_bonds_through_the_sharded_matvec(monkeypatch):
     E, V, _ = eigs.calc_eigs(mps, [[None] * 4], [[None] * 5], 1, 1, oneSite=False, ctx=ctx, shard=spec, return_device=True)
     assert len(spec.made) == 1 and spec.made[0].calls == 1 and spec.made[0].plan.closed     # Dl = Dr = 8: sharded
     assert seen["plan"] is None and seen["native"] is False and seen["consensus"] is not None
-    assert spec.agreed == 2                                                                  # control scalars + the eigenvector
+    assert spec.agreed == 3 and spec.host_agreed == 1          # start vector, control scalars, eigenvector; eigenvalue
     assert E == 1.0 and tuple(V.shape) == (2 * 2 * 8 * 8, 1)
     E, V, _ = eigs.calc_eigs(mps, [[None] * 4], [[None] * 5], 0, 1, oneSite=False, ctx=ctx, shard=spec, return_device=True)
     assert len(spec.made) == 1 and seen["consensus"] is None and seen["plan"] is not None   # Dl = 4 < min_dim: local plan
+    assert spec.agreed == 4 and spec.host_agreed == 2          # ... whose eigenpair is still taken from rank 0
 
 
 def test_shard_spec_keeps_every_rank_a_ket_range():

@@ -8,95 +8,13 @@ import pytest
 torch = pytest.importorskip("torch")
 
 
-class _Ctx:
-    tdtype = torch.complex128
-    device = torch.device("cpu")
-    svd_method = -1
-    svd_ws = None
-
-    def empty(self, *shape):
-        return torch.empty(shape, dtype=self.tdtype)
-
-    def svd_method_for(self, rows, cols):
-        return 0
-
-
-def _permute4(src, out, dims, strides, conj=False, scale=None, scale_axis=0):
-    # pdmrg_permute4: the first prod(dims) elements of `out` receive src[sum_i idx_i * stride_i] (conjugated)
-    if all(st >= 0 for st in strides):
-        view = torch.as_strided(src.reshape(-1), tuple(dims), tuple(strides))
-    else:
-        # negative strides walk back from ``src`` (a view into a larger buffer, e.g. the last row of heevd's output)
-        base = src.as_strided((src.untyped_storage().nbytes() // src.element_size(),), (1,), 0)
-        idx = torch.full(tuple(dims), src.storage_offset(), dtype=torch.int64)
-        for ax, (n, st) in enumerate(zip(dims, strides)):
-            shp = [1] * len(dims)
-            shp[ax] = n
-            idx = idx + (torch.arange(n, dtype=torch.int64) * st).reshape(shp)
-        assert int(idx.min()) >= 0
-        view = base[idx]
-    res = (view.conj() if conj else view).resolve_conj()
-    if scale is not None:                      # out[..., i, ...] *= scale[i] along scale_axis
-        shp = [1] * len(dims)
-        shp[scale_axis] = dims[scale_axis]
-        res = res * scale.reshape(shp).to(res.dtype)
-    res = res.reshape(-1)
-    out.reshape(-1)[: res.numel()].copy_(res)
-    return out
-
-
-def _gemm_nt(A, B, C=None, *, M=None, N=None, K=None, batch=1, lda=None, ldb=None, ldc=None, strideA=0, strideB=0,
-             strideC=0, conjB=False, alpha=1.0, beta=0):
-    assert batch == 1 and beta in (0, 1)
-    if M is None:
-        M, K = A.shape
-        N = B.shape[0]
-        lda = ldb = K
-    a = torch.as_strided(A.reshape(-1), (M, K), (lda, 1))
-    b = torch.as_strided(B.reshape(-1), (N, K), (ldb, 1))
-    r = alpha * (a @ (b.conj() if conjB else b).T)
-    if C is None:
-        return r.contiguous()
-    ldc = N if ldc is None else ldc
-    out = torch.as_strided(C.reshape(-1), (M, N), (ldc, 1))
-    out.copy_(r + out if beta else r)
-    return C
-
-
-def _heevd(a, ws):
-    # pdmrg_heevd: in place, row i of ``a`` <- i-th eigenvector (ascending eigenvalues)
-    w, v = torch.linalg.eigh(a)
-    a.copy_(v.T)
-    return w, a, torch.zeros(1, dtype=torch.int32)
-
-
-def _left_basis(X, ws, keep=0):
-    G = X @ X.conj().T
-    lam, V = torch.linalg.eigh(G)
-    lam, V = lam.flip(0), V.flip(1)
-    return V.T.contiguous(), lam.clamp_min(0.0), torch.zeros(1, dtype=torch.int32)       # rows = eigenvectors u_a
-
-
-def _svd(a, ws, method=0, keep=0):
-    U, S, Vh = torch.linalg.svd(a, full_matrices=False)
-    return U.contiguous(), S.to(torch.float64), Vh.contiguous(), torch.zeros(1, dtype=torch.int32)
-
-
-def _recycle_basis(X1, X2, Wt, k, b, ws, method=None):
-    from oracle import recycle_oracle as R
-    Pt, Ct, S = R.recycle_basis(X1.numpy(), X2.numpy(), Wt.numpy(), int(k), int(b))
-    return torch.from_numpy(np.ascontiguousarray(Pt)), torch.from_numpy(np.ascontiguousarray(Ct)), S, True, 1
+from emu_device import _Ctx, _permute4, _gemm_nt, _left_basis, _svd, _recycle_basis, _heevd, install  # noqa: F401
 
 
 @pytest.fixture
 def T(monkeypatch):
-    from pydmrg_b200 import truncate, device as D
-    monkeypatch.setattr(D, "permute4", _permute4)
-    monkeypatch.setattr(D, "gemm_nt", _gemm_nt)
-    monkeypatch.setattr(D, "left_basis", _left_basis)
-    monkeypatch.setattr(D, "recycle_basis", _recycle_basis)
-    monkeypatch.setattr(D, "svd", _svd)
-    monkeypatch.setattr(D, "heevd", _heevd)
+    from pydmrg_b200 import truncate
+    install(monkeypatch.setattr)
     return truncate
 
 
