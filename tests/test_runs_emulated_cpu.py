@@ -1,0 +1,186 @@
+"""The product's run API (pydmrg_b200.dmrg / idmrg / eigs / env / truncate / contract / mps) executed END TO END
+on the CPU: the device entry points are replaced by the torch-CPU emulations of tests/emu_device.py, everything above
+them -- sweeps, steps, local-solver driver, Python Davidson loop, truncation bookkeeping, state averaging, chi
+schedules, save / load, result packing -- is the product's own code.  The runs are compared with the fixtures the
+UNMODIFIED reference produced (tests/golden/*.npz) and with dense ED.
+
+What this covers: the host layer, every round, without a GPU.  What it does not: the CUDA kernels (``-m gpu``)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+PRM = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)
+
+
+@pytest.fixture
+def E(monkeypatch):
+    import emu_device
+    emu_device.install(monkeypatch.setattr)
+    from pydmrg_b200 import davidson
+    davidson.release_workspaces()
+    yield emu_device
+    davidson.release_workspaces()
+
+
+def rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+# ---- the emulations themselves against the reference's outputs ----------------------------------------------------
+@pytest.mark.parametrize("c", ["a", "b", "c", "d"])
+def test_emulated_entry_points_match_reference_kernels(E, golden, c):
+    from pydmrg_b200 import device as D
+    g = golden["kernels"]
+    ctx = E.Context("c128")
+    L, R, W1, W2 = g[c + "_L"], g[c + "_R"], g[c + "_W1"], g[c + "_W2"]
+    x1, x2 = g[c + "_x1"], g[c + "_x2"]
+    d, Dl, Dr = x1.shape
+    plan = D.HeffPlan(1, d, Dl, Dr, [(ctx.dev(L), D.combine_onesite(W1, L.shape[1], R.shape[1], d, np.complex128), ctx.dev(R))], None)
+    y = torch.empty(x1.size, dtype=torch.complex128)
+    plan.apply(ctx.dev(x1.ravel()), y, -1.0)
+    assert rel(y.numpy(), g[c + "_y1"]) < 1e-13
+    plan = D.HeffPlan(1, d * d, Dl, Dr, [(ctx.dev(L), D.combine_twosite(W1, W2, np.complex128), ctx.dev(R))], None)
+    y = torch.empty(x2.size, dtype=torch.complex128)
+    plan.apply(ctx.dev(x2.ravel()), y, -1.0)
+    assert rel(y.numpy(), g[c + "_y2"]) < 1e-13
+    # ket-range and block-mask restrictions add up to the whole operator (the two sharded modes)
+    parts = torch.zeros_like(y)
+    for k0, kn in ((0, Dl // 2), (Dl // 2, Dl - Dl // 2)):
+        yp = torch.empty_like(y)
+        D.HeffPlan(1, d * d, Dl, Dr, [(ctx.dev(L), D.combine_twosite(W1, W2, np.complex128), ctx.dev(R))], None, k_range=(k0, kn)).apply(
+            ctx.dev(x2.ravel()), yp, -1.0)
+        parts += yp
+    assert rel(parts.numpy(), g[c + "_y2"]) < 1e-13
+    A = ctx.dev(g[c + "_A"])
+    assert rel(D.env_update_right(A, W1, ctx.dev(L), None, None).numpy(), g[c + "_envR_out"]) < 1e-13
+    assert rel(D.env_update_left(A, W1, ctx.dev(R), None, None).numpy(), g[c + "_envL_out"]) < 1e-13
+    assert rel(D.env_update_right(A, W1, ctx.dev(L), ctx.dev(g[c + "_Abra"]), None).numpy(), g[c + "_envR_bra_out"]) < 1e-13
+    assert rel(D.env_update_left(A, None, ctx.dev(R), ctx.dev(g[c + "_Abra"]), None).numpy(), g[c + "_envL_none_out"]) < 1e-13
+
+
+# ---- run_dmrg ------------------------------------------------------------------------------------------------------
+def test_config0_one_site_run(E, golden):
+    """BASELINE configs[0]: TASEP N=10 chi=10 s=-0.5, the reference's own one-site algorithm through the product's
+    run_dmrg: Davidson against the reference's Davidson run (its 1e-7 solver floor), 'exact' against its exact run."""
+    from pydmrg_b200 import dmrg, mpo as M
+    g = golden["runs"]
+    mpo = M.asep_mpo(10, tuple(float(v) for v in g["cfg0_params"]))
+    ctx = E.Context("c128")
+    np.random.seed(0)
+    out = dmrg.run_dmrg(mpo, mbd=10, tol=1e-8, maxIter=10, ctx=ctx, native=False, returnEntSpec=True)
+    assert abs(out[0] - g["cfg0_davidson_E"]) < 1e-7 * abs(g["cfg0_davidson_E"])
+    assert abs(out[0] - g["cfg0_exact_E"]) < 1e-7 * abs(g["cfg0_exact_E"])
+    assert abs(out[1] - g["cfg0_davidson_EE"]) < 1e-6
+    np.random.seed(0)
+    out = dmrg.run_dmrg(mpo, mbd=10, tol=1e-8, maxIter=10, alg="exact", ctx=ctx, recycle=False)
+    assert abs(out[0] - g["cfg0_exact_E"]) < 1e-10 * abs(g["cfg0_exact_E"])
+    assert abs(out[1] - g["cfg0_exact_EE"]) < 1e-8
+
+
+@pytest.mark.parametrize("twoSite", [False, True])
+def test_small_runs_vs_ed_and_reference(E, golden, twoSite):
+    from pydmrg_b200 import contract, dmrg, mpo as M
+    g = golden["runs"]
+    ctx = E.Context("c128")
+    for tag in ("tasep6", "asep6"):
+        prm = tuple(float(v) for v in g[tag + "_params"])
+        mpo = M.asep_mpo(6, prm)
+        np.random.seed(3)
+        out = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=6, ctx=ctx, native=False, twoSite=twoSite, res_tol=1e-11,
+                            returnEntSpec=True, returnState=True)
+        E0, EE, gap, EEs, mps = out
+        assert abs(E0 - g[tag + "_ed_top"]) < 1e-9 * abs(g[tag + "_ed_top"])
+        assert abs(E0 - g[tag + "_dmrg_E"]) < 1e-7 * abs(g[tag + "_dmrg_E"])
+        if not twoSite:
+            assert abs(EE - g[tag + "_dmrg_EE"]) < 1e-6
+        # observables on the returned state (tests/asep/currentCheck.py:29-44)
+        cur = contract.full_contract(mpo=M.asep_curr_mpo(6, prm), mps=mps, ctx=ctx) / contract.full_contract(mps=mps, ctx=ctx)
+        assert abs(cur - g[tag + "_current_rr"]) < 1e-6 * max(1.0, abs(g[tag + "_current_rr"]))
+
+
+@pytest.mark.parametrize("twoSite", [False, True])
+@pytest.mark.parametrize("tag", ["asep6", "asep8"])
+def test_two_states_runs(E, golden, tag, twoSite):
+    """nStates = 2 (every production script of the reference): E and the gap against the reference's run and ED,
+    with the reference's one-site algorithm and with two-site sweeps (state-averaged truncation)."""
+    from pydmrg_b200 import dmrg, mpo as M
+    g = golden["multistate"]
+    N, mbd, seed = (int(v) for v in g[tag + "_cfg"])
+    mpo = M.asep_mpo(N, tuple(float(v) for v in g["params"]))
+    ctx = E.Context("c128")
+    np.random.seed(seed)
+    out = dmrg.run_dmrg(mpo, mbd=mbd, tol=1e-10, maxIter=6, nStates=2, ctx=ctx, native=False, twoSite=twoSite, res_tol=1e-10)
+    ed = g[tag + "_ed"]
+    assert abs(out[0] - ed[0]) < 1e-8 * abs(ed[0])
+    assert abs(out[2] - (ed[0] - ed[1])) < 1e-7 * abs(ed[0])
+    assert abs(out[2] - g[tag + "_gap"]) < 1e-7 * abs(ed[0])
+    if not twoSite:
+        assert abs(out[1] - g[tag + "_EE"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["tasep8", "asep8"])
+def test_left_and_right_eigenstates_run(E, golden, tag):
+    """run_dmrg(calcLeftState=True) against the reference's run (tests/golden/leftright.npz): eigenvalue, both
+    entropies, current and energy <l|O|r>/<l|r> through the product's full_contract."""
+    from pydmrg_b200 import contract, dmrg, mpo as M
+    g = golden["leftright"]
+    N, mbd, seed = (int(v) for v in g[tag + "_cfg"])
+    prm = tuple(float(v) for v in g[tag + "_params"])
+    mpo = M.asep_mpo(N, prm)
+    ctx = E.Context("c128")
+    np.random.seed(seed)
+    E0, EE, gap, mps = dmrg.run_dmrg(mpo, mbd=mbd, tol=1e-12, maxIter=6, res_tol=1e-11, calcLeftState=True, returnState=True,
+                                     ctx=ctx, native=False)
+    r, l = mps
+    scale = abs(g[tag + "_ed_top"])
+    assert abs(E0 - g[tag + "_ed_top"]) < 1e-9 * scale and abs(E0 - g[tag + "_E"]) < 1e-7 * scale
+    assert abs(EE[0] - g[tag + "_EE"]) < 1e-6 and abs(EE[1] - g[tag + "_EEl"]) < 1e-6
+    den = contract.full_contract(mps=r, lmps=l, ctx=ctx)
+    cur = contract.full_contract(mpo=M.asep_curr_mpo(N, prm), mps=r, lmps=l, ctx=ctx) / den
+    ene = contract.full_contract(mpo=mpo, mps=r, lmps=l, ctx=ctx) / den
+    assert abs(cur - g[tag + "_current_lr"]) < 1e-6 * max(1.0, abs(g[tag + "_current_lr"]))
+    assert abs(ene - g[tag + "_ed_top"]) < 1e-8 * scale
+
+
+def test_chi_schedule_with_saved_states(E, golden, tmp_path):
+    """mbd=[4, 8, 16] continued through files (dmrg.py:352-358): arrays over chi in the reference's return packing."""
+    from pydmrg_b200 import dmrg, mpo as M, mps as mps_tools
+    g = golden["leftright"]
+    N, seed = (int(v) for v in g["sched_cfg"])
+    mpo = M.asep_mpo(N, tuple(float(v) for v in g["asep8_params"]))
+    ctx = E.Context("c128")
+    np.random.seed(seed)
+    fname = str(tmp_path / "st")
+    Evec, EEvec, gapvec = dmrg.run_dmrg(mpo, mbd=[4, 8, 16], tol=1e-10, maxIter=4, fname=fname, ctx=ctx, native=False)
+    assert Evec.shape == (3,) and np.all(np.isnan(gapvec))
+    assert np.max(np.abs(Evec - g["sched_E"]) / np.abs(g["sched_E"])) < 2e-7
+    assert np.max(np.abs(EEvec - g["sched_EE"])) < 1e-5
+    mpsL, gs = mps_tools.load_mps(fname + "_mbd2")
+    assert int(gs) == N // 2 + 1 and len(mpsL[0]) == N and max(max(t.shape) for t in mpsL[0]) == 16
+
+
+def test_idmrg_run(E, golden):
+    from pydmrg_b200 import idmrg, mpo as M
+    g = golden["runs"]
+    ctx = E.Context("c128")
+    mpo4 = M.asep_mpo(4, (0.2, 0.8, 0.1, 0.9, 0.4, 0.6, -0.5))
+    np.random.seed(5)
+    out = idmrg.run_idmrg(mpo4, mbd=10, maxIter=20, returnEntSpec=True, ctx=ctx, native=False)
+    assert abs(out[0] - g["idmrg_E"]) < 1e-6 * abs(g["idmrg_E"])
+    assert abs(out[1] - g["idmrg_EE"]) < 1e-6
+
+
+def test_f64_context_heisenberg_two_site(E):
+    """dtype='f64' host path (real Ritz pairs forced, real tensors end to end) against the complex oracle run."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import dmrg, mpo as M
+    mpo = M.heisenberg_mpo(10)
+    ctx = E.Context("f64")
+    np.random.seed(2)
+    out = dmrg.run_dmrg(mpo, mbd=16, tol=1e-10, maxIter=4, twoSite=True, dtype="f64", ctx=ctx, native=False, res_tol=1e-10)
+    np.random.seed(2)
+    Eo = orc.run_dmrg_twosite(mpo, 16, n_sweeps=5)[0]
+    assert abs(out[0] - Eo) < 1e-8 * abs(Eo) and abs(np.imag(out[0])) == 0
