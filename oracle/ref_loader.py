@@ -93,6 +93,12 @@ def _h5py_shim():
         def get(self, key):
             return self._store.get(key)
 
+        def __getitem__(self, key):
+            return self._store[key]
+
+        def __contains__(self, key):                            # a dataset, or a group (prefix of dataset paths)
+            return key in self._store or any(k.startswith(key + "/") for k in self._store)
+
         def __enter__(self):
             return self
 

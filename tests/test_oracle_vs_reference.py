@@ -91,3 +91,20 @@ def test_full_contract_matches_reference(ref):
         b = ref.contract.full_contract(mps=[mps])
     assert abs(a - orc.full_contract(mpo, mps, lmps)) < 1e-12 * abs(a)
     assert abs(b - orc.full_contract(None, mps)) < 1e-12 * abs(b)
+
+
+def test_saved_states_round_trip_between_reference_and_product(ref, tmp_path):
+    """saved_states plug in unchanged (north-star): a state written by the reference's save_mps (HDF5 layout of
+    tools/mps_tools.py:364-373, NPZ layout :355-362) is read by the product's load_mps and vice versa."""
+    from pydmrg_b200 import mps as mps_tools
+    rng = np.random.default_rng(0)
+    mpsL = [[rng.standard_normal(s) + 1j * rng.standard_normal(s) for s in ((2, 1, 2), (2, 2, 4), (2, 4, 2), (2, 2, 1))]
+            for _ in range(2)]
+    for fmt in ("hdf5", "npz"):
+        a, b = str(tmp_path / ("ref_" + fmt)), str(tmp_path / ("prod_" + fmt))
+        ref.mps_tools.save_mps(mpsL, a, gaugeSite=2, fformat=fmt)
+        got, gs = mps_tools.load_mps(a, fformat=fmt)
+        assert int(gs) == 2 and all(np.array_equal(x, y) for s in range(2) for x, y in zip(got[s], mpsL[s]))
+        mps_tools.save_mps(mpsL, b, gaugeSite=3, fformat=fmt)
+        got, gs = ref.mps_tools.load_mps(b, fformat=fmt)
+        assert int(gs) == 3 and all(np.array_equal(x, y) for s in range(2) for x, y in zip(got[s], mpsL[s]))
