@@ -177,3 +177,61 @@ def test_sharded_two_site_sweeps_stay_in_lockstep_on_two_gloo_ranks():
     # convergence test on one rank left the ranks 1e-9 apart and cost 40 % more mat-vecs and 1e-8 in E)
     assert abs(two[0][0] - single[0]) < 1e-11 * abs(single[0])
     assert abs(two[0][1] - single[1]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# s-field scan (BASELINE configs[3]) on two gloo ranks
+# ---------------------------------------------------------------------------------------------------------------
+def _scan_worker(rank, world, port, q, continuation):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emu_device
+    emu_device.install(setattr)
+    from pydmrg_b200 import mpo as M, scan
+    s_vals = np.linspace(-0.5, 0.5, 5)
+    mpo_of = lambda s: M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    np.random.seed(7 + rank)
+    res = scan.run_scan(mpo_of, s_vals, 8, rank, world, dist, ramp=(4,), tol=1e-10, maxIter=4, continuation=continuation,
+                        ctx=emu_device.Context("c128"), native=False, res_tol=1e-10)
+    q.put((rank, res["E"], res["EE"], res["points"]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("continuation", [False, True])
+def test_s_scan_on_two_gloo_ranks(continuation):
+    """pydmrg_b200.scan.run_scan: the points are dealt to two ranks (every second point for cold starts, contiguous
+    blocks with warm starts inside a block for ``continuation``), no data-path collective, one gather; every rank
+    ends with the full curve, which matches dense diagonalisation of the tilted generator at every s."""
+    import torch.multiprocessing as mp
+    from pydmrg_b200 import mpo as M
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + (os.getpid() % 1500) + int(continuation)
+    ps = [ctx.Process(target=_scan_worker, args=(r, 2, port, q, continuation)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict((r[0], r[1:]) for r in (q.get(timeout=600) for _ in ps))
+    for p in ps:
+        p.join(timeout=60)
+    s_vals = np.linspace(-0.5, 0.5, 5)
+    exact = []
+    for s in s_vals:
+        op = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))[0]
+        T = op[0][0]
+        for W in op[1:]:
+            T = np.einsum("a...,abij->b...ij", T, W)
+        T = T[0]
+        idx = list(range(0, 12, 2)) + list(range(1, 12, 2))
+        ev = np.linalg.eigvals(T.transpose(idx).reshape(64, 64))
+        exact.append(ev[np.argmax(ev.real)])
+    exact = np.array(exact)
+    assert sorted(res[0][2] + res[1][2]) == [0, 1, 2, 3, 4]
+    assert res[0][2] == ([0, 1, 2] if continuation else [0, 2, 4])
+    for rank in (0, 1):
+        assert np.array_equal(res[rank][0], res[0][0])
+        assert np.max(np.abs(res[rank][0] - exact)) < 1e-9          # the eigenvalue at s = 0 is exactly 0: absolute
