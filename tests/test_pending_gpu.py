@@ -112,3 +112,33 @@ def test_column_restricted_block_updates(P, dtype, dims):
         assert not bool(torch.isnan(torch.view_as_real(out) if out.is_complex() else out).any())
         err = (out - full).abs().max().item() / full.abs().max().item()
         assert err < 1e-13, (direction, err)
+
+
+def test_gauge_utilities_on_device(P):
+    """gauge.make_mps_right / move_gauge / calc_entanglement_all on the device against the host (NumPy) routines."""
+    from pydmrg_b200 import gauge, mps as mps_tools
+    c = P.core.Context("c128")
+    N = 10
+    np.random.seed(8)
+    mps = [t + 0.2j * np.random.rand(*t.shape) for t in mps_tools.create_rand_mps(N, 24)]
+
+    def dense(m):
+        v = np.asarray(m[0])[:, 0, :]
+        for t in m[1:]:
+            v = np.einsum("...a,pab->...pb", v, np.asarray(t))
+        return v[..., 0].reshape(-1)
+
+    psi0 = dense(mps)
+    right = gauge.make_mps_right([t.copy() for t in mps], ctx=c)
+    assert np.allclose(dense(right), psi0, atol=1e-12 * np.abs(psi0).max())
+    for t in right[1:]:
+        assert np.allclose(np.einsum("pab,pcb->ac", t, t.conj()), np.eye(t.shape[1]), atol=1e-12)
+    moved = gauge.move_gauge([c.dev(t) for t in right], 0, 6, ctx=c)          # device in, device out
+    assert all(hasattr(t, "is_cuda") and t.is_cuda for t in moved)
+    assert np.allclose(dense([c.host(t) for t in moved]), psi0, atol=1e-12 * np.abs(psi0).max())
+    EE = gauge.calc_entanglement_all([[t.copy() for t in right]], gSite=0, ctx=c)
+    psi = psi0 / np.linalg.norm(psi0)
+    for b in range(N - 1):
+        s = np.linalg.svd(psi.reshape(2 ** (b + 1), -1), compute_uv=False)
+        p = s[s > 1e-15] ** 2
+        assert abs(EE[0, b] - np.sum(-p * np.log2(p))) < 1e-9

@@ -184,3 +184,42 @@ def test_f64_context_heisenberg_two_site(E):
     np.random.seed(2)
     Eo = orc.run_dmrg_twosite(mpo, 16, n_sweeps=5)[0]
     assert abs(out[0] - Eo) < 1e-8 * abs(Eo) and abs(np.imag(out[0])) == 0
+
+
+# ---- gauge utilities ----------------------------------------------------------------------------------
+def _dense_state(mps):
+    v = np.asarray(mps[0])[:, 0, :]                              # (d, D1)
+    for t in mps[1:]:
+        v = np.einsum("...a,pab->...pb", v, np.asarray(t))
+    return v[..., 0].reshape(-1)
+
+
+def test_gauge_utilities(E):
+    """gauge.move_gauge_* / make_mps_right / calc_entanglement_all (tools/mps_tools.py:36-96,
+    tools/aux/process_states.py:5-27): the state is unchanged, the sites left behind are isometries, and the entropy of
+    every bond equals the one of the dense bipartition."""
+    from pydmrg_b200 import gauge, mps as mps_tools
+    ctx = E.Context("c128")
+    N = 7
+    np.random.seed(4)
+    mps = [t + 0.3j * np.random.rand(*t.shape) for t in mps_tools.create_rand_mps(N, 6)]
+    psi0 = _dense_state(mps)
+    right = gauge.make_mps_right([t.copy() for t in mps], ctx=ctx)
+    assert isinstance(right[0], np.ndarray)
+    assert np.allclose(_dense_state(right), psi0, atol=1e-14 * np.abs(psi0).max() * 100)
+    for t in right[1:]:
+        assert np.allclose(np.einsum("pab,pcb->ac", t, t.conj()), np.eye(t.shape[1]), atol=1e-12)
+    ref = mps_tools.make_mps_right([t.copy() for t in mps])      # the host restatement of the reference's routine
+    assert np.allclose(np.abs(np.vdot(_dense_state(ref), _dense_state(right))), np.vdot(psi0, psi0).real, rtol=1e-12)
+    moved = gauge.move_gauge([t.copy() for t in right], 0, 4, ctx=ctx)
+    assert np.allclose(_dense_state(moved), psi0, atol=1e-12 * np.abs(psi0).max())
+    for t in moved[:4]:
+        assert np.allclose(np.einsum("pab,pac->bc", t.conj(), t), np.eye(t.shape[2]), atol=1e-12)
+    back = gauge.move_gauge(moved, 4, 1, ctx=ctx)
+    assert np.allclose(_dense_state(back), psi0, atol=1e-12 * np.abs(psi0).max())
+    EE = gauge.calc_entanglement_all([[t.copy() for t in right]], gSite=0, ctx=ctx)
+    psi = psi0 / np.linalg.norm(psi0)
+    for b in range(N - 1):
+        s = np.linalg.svd(psi.reshape(2 ** (b + 1), -1), compute_uv=False)
+        p = s[s > 1e-15] ** 2
+        assert abs(EE[0, b] - np.sum(-p * np.log2(p))) < 1e-10
