@@ -354,12 +354,23 @@ extern "C" int pdmrg_vec_project(int dtype, long long n, int m, const void* X, l
   PDMRG_REQUIRE(scratch_bytes >= pdmrg_vec_scratch_bytes(m), "pdmrg_vec_project: scratch too small");
   PDMRG_REQUIRE(n > 0 && m >= 0, "pdmrg_vec_project: bad extents");
   const bool cplx = dtype == PDMRG_C128;
+  const int E = cplx ? 2 : 1;
   const int grid = vec_grid(n);
   double* partial = static_cast<double*>(scratch);
-  if (cplx) project_kernel<true><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial, norm2_dev, ticket_of(scratch));
-  else project_kernel<false><<<grid, VT, 0, stream>>>(n, m, (const double*)X, stride, (const double*)c_dev, scale_dev, (double*)r, partial, norm2_dev, ticket_of(scratch));
-  PDMRG_CHECK_LAUNCH();
-  count_launch();
+  // the kernel stages at most MAXM coefficients in shared memory: larger subspaces (nroots >= 2: up to 12 + 4*nroots
+  // vectors) go in passes of MAXM; the scaling and the norm that is kept belong to the last pass
+  int i0 = 0;
+  do {
+    const int mm = (m - i0) < MAXM ? (m - i0) : MAXM;
+    const bool last = i0 + mm >= m;
+    const double* Xp = static_cast<const double*>(X) + (size_t)E * i0 * stride;
+    const double* cp = static_cast<const double*>(c_dev) + (size_t)E * i0;
+    if (cplx) project_kernel<true><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, cp, last ? scale_dev : nullptr, (double*)r, partial, norm2_dev, ticket_of(scratch));
+    else project_kernel<false><<<grid, VT, 0, stream>>>(n, mm, Xp, stride, cp, last ? scale_dev : nullptr, (double*)r, partial, norm2_dev, ticket_of(scratch));
+    PDMRG_CHECK_LAUNCH();
+    count_launch();
+    i0 += mm;
+  } while (i0 < m);
   return 0;
 }
 
