@@ -46,8 +46,9 @@ class DavidsonWorkspace:
         self.R = torch.empty((2 * nroots + 2, n), dtype=dt, device=device)   # residual / Ritz vectors
         self.small = torch.zeros(2 * rows * (nroots + 2) + 16, dtype=dt, device=device)
         self.norms = torch.zeros(2 * nroots + 16, dtype=torch.float64, device=device)
-        self.native_scratch = torch.zeros(int(lib.pdmrg_davidson_scratch_bytes(nroots, 12)) + 256, dtype=torch.uint8,
-                                          device=device)
+        # scratch of the C++ loop for the largest subspace these slabs can hold (rows = max_space + 4 * nroots)
+        self.native_scratch = torch.zeros(int(lib.pdmrg_davidson_scratch_bytes(nroots, max(12, rows - 4 * nroots))) + 256,
+                                          dtype=torch.uint8, device=device)
         self._ops = {}
 
     def ops(self, n):

@@ -235,3 +235,27 @@ def test_s_scan_on_two_gloo_ranks(continuation):
     for rank in (0, 1):
         assert np.array_equal(res[rank][0], res[0][0])
         assert np.max(np.abs(res[rank][0] - exact)) < 1e-9          # the eigenvalue at s = 0 is exactly 0: absolute
+
+
+def test_larger_davidson_subspace_needs_fewer_matvecs(monkeypatch, golden):
+    """``max_space`` (solver option of run_dmrg / calc_eigs): same eigenpair, fewer restarts."""
+    from emu_device import install
+    from oracle import dmrg_oracle as orc
+    install(monkeypatch.setattr)
+    from pydmrg_b200 import davidson as dav
+    g = golden["davidson"]
+    L, R, W, x0 = g["L"], g["R"], g["W"], g["x0"]
+
+    def matvec(x, y):
+        y.copy_(torch.from_numpy(orc.heff_onesite(x.numpy(), [L], [W], [R], x0.shape)))
+
+    out = {}
+    for ms in (12, 24):
+        dav.release_workspaces()
+        st = {}
+        e, vecs = dav.davidson(matvec, [torch.from_numpy(x0.ravel().copy())], x0.size, 1, torch.device("cpu"), nroots=1, stats=st,
+                               native=False, max_space=ms)
+        out[ms] = (e[0], st["n_matvec"])
+    dav.release_workspaces()
+    assert abs(out[24][0] - out[12][0]) < 1e-7 * abs(out[12][0])
+    assert out[24][1] < out[12][1]
