@@ -229,6 +229,28 @@ int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const 
                    void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
                    double* e_out_host, void* vecs_out, long long vecs_stride,
                    int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream);
+/* The same loop with a diagonal preconditioner in the correction step (opt-in: iteration counts then differ from
+ * the reference, whose preconditioner is the identity, tools/diag_tools.py:137-139; it acts at la_tools.py:510):
+ *   t = r / (diag - theta),  |diag_i - theta| kept >= pc_floor * max(1, |theta|),
+ * `diag` = diagonal of the operator sign * H_eff (n elements of dtype, e.g. from pdmrg_heff_diag with the same sign).
+ * Safeguard: if the residual is not halved within two restart periods the loop continues with the identity. */
+int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs, double sign,
+                           int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
+                           double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                           void* XS, void* AX, void* Rv, long long stride,
+                           void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
+                           double* e_out_host, void* vecs_out, long long vecs_stride,
+                           int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
+                           const void* diag, double pc_floor);
+/* r <- r / (diag - theta) element-wise with the floor above; norm2_dev[0] = ||r||^2 of the result.  scratch as for the
+ * other vector kernels (pdmrg_vec_scratch_bytes). */
+int pdmrg_vec_precond(int dtype, long long n, void* r, const void* diag, double theta_re, double theta_im,
+                      double floor_abs, double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream);
+/* diag[p,k,s] (+)= sign * sum_{j,o} L[k,j,k] Wpp[p,j,o] R[s,o,s]: diagonal of one MPO term of H_eff (H1/H2 with
+ * P = d or d1*d2); Wpp (P, wL, wR) on the DEVICE holds the physical-diagonal blocks Wc[(j,p),(o,p)] of the combined
+ * local operator.  accumulate != 0 adds to `out` (several MPO terms). */
+int pdmrg_heff_diag(int dtype, int P, int Dl, int Dr, int wL, int wR, const void* L, const void* R,
+                    const void* Wpp_dev, double sign, int accumulate, void* out, void* stream);
 /* eigenvalues w (n complex) and unit-norm right eigenvectors (columns of v) of a small general
  * complex matrix, column-major interleaved; host only (no GPU needed) */
 int pdmrg_host_eig(int n, const double* a_colmajor_interleaved, double* w_out, double* v_out);

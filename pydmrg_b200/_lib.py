@@ -74,6 +74,10 @@ def _load():
         "pdmrg_davidson_scratch_bytes": (sz, [i, i]),
         "pdmrg_davidson": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz, vp, sz,
                                POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp]),
+        "pdmrg_davidson_precond": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
+                                       vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d]),
+        "pdmrg_vec_precond": (i, [i, ll, vp, vp, d, d, d, vp, vp, sz, vp]),
+        "pdmrg_heff_diag": (i, [i, i, i, i, i, i, vp, vp, vp, d, i, vp, vp]),
         "pdmrg_host_eig": (i, [i, POINTER(d), POINTER(d), POINTER(d)]),
         "pdmrg_svd_workspace_bytes": (sz, [i, i, i, i]),
         "pdmrg_svd": (i, [i, i, i, vp, vp, vp, vp, i, vp, sz, vp, vp]),

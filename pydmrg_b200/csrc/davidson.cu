@@ -186,13 +186,15 @@ extern "C" size_t pdmrg_davidson_scratch_bytes(int nroots, int max_space) {
 }
 
 // XS, AX: (rows >= max_space + 4*nroots) x stride slabs;  Rv: (2*nroots + 2) x stride;  x0: nx0 vectors at x0 + i*x0_stride
-extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, const void* const* Rs, double sign,
-                              int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
-                              double lindep, double res_tol, int max_cycle, int fixed_cycles,
-                              void* XS_, void* AX_, void* Rv_, long long stride,
-                              void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
-                              double* e_out_host, void* vecs_out, long long vecs_stride,
-                              int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_) {
+// diag (optional): diagonal of the operator (sign included) -> correction t = r / (diag - theta) instead of t = r
+static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const void* const* Rs, double sign,
+                         int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
+                         double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                         void* XS_, void* AX_, void* Rv_, long long stride,
+                         void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
+                         double* e_out_host, void* vecs_out, long long vecs_stride,
+                         int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
+                         const void* diag, double pc_floor) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(plan != nullptr, "pdmrg_davidson: null plan");
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_davidson: bad dtype");
@@ -248,6 +250,9 @@ extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, cons
   for (int i = 0; i < nx0; ++i) x0v.push_back(static_cast<const double*>(x0) + (size_t)E * i * x0_stride);
   double last_res = 0.0;
   std::vector<double> coef;
+  bool use_pc = diag != nullptr;
+  double pc_best = 1e300;
+  int pc_stall = 0;
 
   for (cyc = 0; cyc < max_cycle; ++cyc) {
     if (fresh) {
@@ -309,9 +314,16 @@ extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, cons
       }
       double eh[2] = {e[k].real(), e[k].imag()};
       if (pdmrg_davidson_residual(dtype, n, space, coef.data(), eh, XS, AX, stride, rv(k), norms + 2 * k, vscratch, vsb, stream)) return 1;
+      const double* scale_slot = norms + 2 * k;                       // ||r||^2: the projected direction starts from r / ||r||
+      if (use_pc) {                                                       // ... or from t / ||t||, t = r / (diag - theta)
+        double* tn = norms + 2 * nroots + 8 + k;
+        if (pdmrg_vec_precond(dtype, n, rv(k), diag, e[k].real(), e[k].imag(), pc_floor * std::max(1.0, std::abs(e[k])), tn,
+                              vscratch, vsb, stream)) return 1;
+        scale_slot = tn;
+      }
       double* cdev = small + (size_t)E * (2 * rows * (nroots + 2));
       if (pdmrg_vec_dots(dtype, n, space, XS, stride, rv(k), cdev, vscratch, vsb, stream)) return 1;
-      if (pdmrg_vec_project(dtype, n, space, XS, stride, cdev, norms + 2 * k, rv(k), norms + 2 * k + 1, vscratch, vsb, stream)) return 1;
+      if (pdmrg_vec_project(dtype, n, space, XS, stride, cdev, scale_slot, rv(k), norms + 2 * k + 1, vscratch, vsb, stream)) return 1;
     }
     PDMRG_CHECK_CUDA(cudaMemcpyAsync(pin, norms, (size_t)2 * nr * 8, cudaMemcpyDeviceToHost, stream));
     PDMRG_CHECK_CUDA(cudaStreamSynchronize(stream));                       // D2H #2 of the cycle
@@ -322,6 +334,12 @@ extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, cons
       const double dx2 = pin[2 * k], px2 = pin[2 * k + 1];
       if (std::sqrt(std::max(dx2, 0.0)) > last_res) last_res = std::sqrt(std::max(dx2, 0.0));
       if (dx2 > thresh2 && px2 > lindep) keep.push_back(k);                 // la_tools.py:505-537
+    }
+    if (use_pc) {
+      // safeguard: a diagonal that is a poor model of the operator (no diagonal dominance) can stall the restarted
+      // iteration; without a halving of the residual within two restart periods the identity takes over for good
+      if (last_res < 0.5 * pc_best) { pc_best = last_res; pc_stall = 0; }
+      else if (++pc_stall > 2 * ms) use_pc = false;
     }
     if (keep.empty()) { ++cyc; break; }                                     // la_tools.py:539-541
     if (fixed_cycles > 0 && cyc + 1 >= fixed_cycles) { ++cyc; break; }
@@ -360,4 +378,30 @@ extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, cons
   if (cycles_out) *cycles_out = cyc;
   if (last_res_out) *last_res_out = last_res;
   return 0;
+}
+
+extern "C" int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* Ls, const void* const* Rs, double sign,
+                              int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
+                              double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                              void* XS_, void* AX_, void* Rv_, long long stride,
+                              void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
+                              double* e_out_host, void* vecs_out, long long vecs_stride,
+                              int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_) {
+  return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
+                       fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
+                       vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, nullptr, 0.0);
+}
+
+extern "C" int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* Ls, const void* const* Rs, double sign,
+                                      int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots,
+                                      int max_space, double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                                      void* XS_, void* AX_, void* Rv_, long long stride,
+                                      void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
+                                      double* e_out_host, void* vecs_out, long long vecs_stride,
+                                      int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
+                                      const void* diag, double pc_floor) {
+  PDMRG_REQUIRE(diag != nullptr && pc_floor > 0.0, "pdmrg_davidson_precond: needs the operator diagonal and a positive floor");
+  return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
+                       fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
+                       vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor);
 }

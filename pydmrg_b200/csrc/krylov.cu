@@ -229,6 +229,41 @@ project_kernel(long long n, int m, const double* __restrict__ X, long long strid
   last_block_reduce(partial, gridDim.x, 1, norm2_out, ticket);
 }
 
+// t = r / (d - theta), |d - theta| kept >= floor (direction of d - theta preserved); norm2_out = ||t||^2.
+// The diagonal (Jacobi-Davidson style) preconditioner of the Davidson correction step (the reference passes the
+// identity, tools/diag_tools.py:137-139; la_tools.py:510 is where a preconditioner acts).
+template <bool CPLX>
+__global__ void __launch_bounds__(VT)
+precond_kernel(long long n, double* __restrict__ r, const double* __restrict__ diag, double th_re, double th_im, double floor_,
+               double* partial, double* __restrict__ norm2_out, unsigned int* ticket) {
+  double nrm[1] = {0.0};
+  for (long long e = blockIdx.x * (long long)VT + threadIdx.x; e < n; e += (long long)gridDim.x * VT) {
+    if (CPLX) {
+      const double2 d = reinterpret_cast<const double2*>(diag)[e];
+      double dr = d.x - th_re, di = d.y - th_im;
+      const double a = sqrt(dr * dr + di * di);
+      if (a < floor_) {
+        if (a > 0.0) { dr *= floor_ / a; di *= floor_ / a; } else { dr = floor_; di = 0.0; }
+      }
+      const double inv = 1.0 / (dr * dr + di * di);
+      const double2 v = reinterpret_cast<double2*>(r)[e];
+      double2 t;                                                    // v * conj(den) / |den|^2
+      t.x = (v.x * dr + v.y * di) * inv;
+      t.y = (v.y * dr - v.x * di) * inv;
+      reinterpret_cast<double2*>(r)[e] = t;
+      nrm[0] = fma(t.x, t.x, nrm[0]); nrm[0] = fma(t.y, t.y, nrm[0]);
+    } else {
+      double den = diag[e] - th_re;
+      if (fabs(den) < floor_) den = den < 0.0 ? -floor_ : floor_;
+      const double t = r[e] / den;
+      r[e] = t;
+      nrm[0] = fma(t, t, nrm[0]);
+    }
+  }
+  block_reduce_store<1>(nrm, 1, partial);
+  last_block_reduce(partial, gridDim.x, 1, norm2_out, ticket);
+}
+
 template <bool CPLX>
 __global__ void __launch_bounds__(VT)
 normalize_kernel(long long n, const double* __restrict__ in, const double* __restrict__ norm2, double* __restrict__ out) {
@@ -381,6 +416,20 @@ extern "C" int pdmrg_vec_normalize(int dtype, long long n, const void* in, const
   const int grid = vec_grid(dtype == PDMRG_C128 ? 2 * n : n);
   if (dtype == PDMRG_C128) normalize_kernel<true><<<grid, VT, 0, stream>>>(n, (const double*)in, norm2_dev, (double*)out);
   else normalize_kernel<false><<<grid, VT, 0, stream>>>(n, (const double*)in, norm2_dev, (double*)out);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
+  return 0;
+}
+
+extern "C" int pdmrg_vec_precond(int dtype, long long n, void* r, const void* diag, double theta_re, double theta_im,
+                                 double floor_abs, double* norm2_dev, void* scratch, size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(scratch_bytes >= pdmrg_vec_scratch_bytes(1), "pdmrg_vec_precond: scratch too small");
+  PDMRG_REQUIRE(n > 0 && floor_abs > 0.0, "pdmrg_vec_precond: bad extent / floor");
+  const int grid = vec_grid(n);
+  double* partial = static_cast<double*>(scratch);
+  if (dtype == PDMRG_C128) precond_kernel<true><<<grid, VT, 0, stream>>>(n, (double*)r, (const double*)diag, theta_re, theta_im, floor_abs, partial, norm2_dev, ticket_of(scratch));
+  else precond_kernel<false><<<grid, VT, 0, stream>>>(n, (double*)r, (const double*)diag, theta_re, 0.0, floor_abs, partial, norm2_dev, ticket_of(scratch));
   PDMRG_CHECK_LAUNCH();
   count_launch();
   return 0;

@@ -166,3 +166,55 @@ extern "C" int pdmrg_permute4(int dtype, const void* in, void* out, int n0, int 
   count_launch();
   return 0;
 }
+
+// ---- diagonal of the effective Hamiltonian (for the diagonal Davidson preconditioner) ----------------------------
+//   diag[p,k,s] (+)= sign * sum_{j,o} L[k,j,k] * Wpp[p,j,o] * R[s,o,s],   Wpp[p,j,o] = Wc[(j,p),(o,p)]
+namespace pdmrg {
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+heff_diag_kernel(int P, int Dl, int Dr, int wL, int wR, const double* __restrict__ L, const double* __restrict__ R,
+                 const double* __restrict__ Wpp, double sign, int accumulate, double* __restrict__ out) {
+  constexpr int E = CPLX ? 2 : 1;
+  const long long total = (long long)Dl * Dr;
+  for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const int k = (int)(t / Dr), s = (int)(t % Dr);
+    for (int p = 0; p < P; ++p) {
+      double ar = 0.0, ai = 0.0;
+      for (int j = 0; j < wL; ++j) {
+        const double* lp = L + (size_t)E * (((size_t)k * wL + j) * Dl + k);          // L[k,j,k]
+        const double lr = lp[0], li = CPLX ? lp[1] : 0.0;
+        double br = 0.0, bi = 0.0;                                                    // sum_o Wpp[p,j,o] R[s,o,s]
+        for (int o = 0; o < wR; ++o) {
+          const double* wp = Wpp + (size_t)E * (((size_t)p * wL + j) * wR + o);
+          const double wr_ = wp[0], wi = CPLX ? wp[1] : 0.0;
+          if (wr_ == 0.0 && wi == 0.0) continue;
+          const double* rp = R + (size_t)E * (((size_t)s * wR + o) * Dr + s);        // R[s,o,s]
+          const double rr = rp[0], ri = CPLX ? rp[1] : 0.0;
+          br += wr_ * rr - wi * ri;
+          bi += wr_ * ri + wi * rr;
+        }
+        ar += lr * br - li * bi;
+        ai += lr * bi + li * br;
+      }
+      double* op = out + (size_t)E * (((size_t)p * Dl + k) * Dr + s);
+      if (accumulate) { op[0] += sign * ar; if (CPLX) op[1] += sign * ai; }
+      else { op[0] = sign * ar; if (CPLX) op[1] = sign * ai; }
+    }
+  }
+}
+}  // namespace pdmrg
+
+extern "C" int pdmrg_heff_diag(int dtype, int P, int Dl, int Dr, int wL, int wR, const void* L, const void* R,
+                               const void* Wpp_dev, double sign, int accumulate, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_heff_diag: bad dtype");
+  PDMRG_REQUIRE(P > 0 && Dl > 0 && Dr > 0 && wL > 0 && wR > 0, "pdmrg_heff_diag: bad extents");
+  const int grid = grid_for((long long)Dl * Dr, 256);
+  if (dtype == PDMRG_C128)
+    heff_diag_kernel<true><<<grid, 256, 0, stream>>>(P, Dl, Dr, wL, wR, (const double*)L, (const double*)R, (const double*)Wpp_dev, sign, accumulate, (double*)out);
+  else
+    heff_diag_kernel<false><<<grid, 256, 0, stream>>>(P, Dl, Dr, wL, wR, (const double*)L, (const double*)R, (const double*)Wpp_dev, sign, accumulate, (double*)out);
+  PDMRG_CHECK_LAUNCH();
+  count_launch();
+  return 0;
+}

@@ -96,7 +96,7 @@ def _orthonormalise(ops, src, dst, norm_slot, small):
 
 
 def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
-                    res_tol=None, fixed_cycles=None, stats=None, sign=-1.0):
+                    res_tol=None, fixed_cycles=None, stats=None, sign=-1.0, diag=None, precond_floor=0.1):
     """The same solver sequenced in C++ (csrc/davidson.cu, ``pdmrg_davidson``): one C-ABI call per
     local eigenproblem, operator = ``sign`` * H_eff of ``plan``."""
     ms = max_space + 3 * nroots
@@ -108,12 +108,15 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
     e_host = (ctypes.c_double * (2 * nroots))()
     n_mv, cyc, last = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
     ws = plan.workspace.get(plan.ws_bytes)
-    check(lib.pdmrg_davidson(plan._plan, plan._Lp, plan._Rp, float(sign), code, n, D._ptr(W.R[nroots]), W.R.stride(0),
-                             len(x0), nroots, max_space, float(lindep), -1.0 if res_tol is None else float(res_tol),
-                             int(max_cycle), int(fixed_cycles or 0), D._ptr(W.XS), D._ptr(W.AX), D._ptr(W.R),
-                             W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
-                             e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last),
-                             D._stream()), "pdmrg_davidson")
+    args = (plan._plan, plan._Lp, plan._Rp, float(sign), code, n, D._ptr(W.R[nroots]), W.R.stride(0),
+            len(x0), nroots, max_space, float(lindep), -1.0 if res_tol is None else float(res_tol),
+            int(max_cycle), int(fixed_cycles or 0), D._ptr(W.XS), D._ptr(W.AX), D._ptr(W.R),
+            W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
+            e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), D._stream())
+    if diag is None:
+        check(lib.pdmrg_davidson(*args), "pdmrg_davidson")
+    else:
+        check(lib.pdmrg_davidson_precond(*args, D._ptr(diag), float(precond_floor)), "pdmrg_davidson_precond")
     plan.n_apply += n_mv.value
     nr = min(nroots, max(1, min(nroots, n)))
     e = np.array([complex(e_host[2 * k], e_host[2 * k + 1]) for k in range(nr)])
@@ -125,7 +128,8 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
 
 
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
-             res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None):
+             res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None, diag=None,
+             precond_floor=0.1):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
@@ -134,6 +138,9 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     ||r||^2 <= lindep.  ``fixed_cycles``: stop after exactly that many cycles (benchmarking).
     When the H_eff ``plan`` is given the loop runs in C++ (``pdmrg_davidson``) unless
     ``native=False`` / PDMRG_PY_DAVIDSON=1; this Python loop is the specification it mirrors.
+    ``diag``: diagonal of the operator (device vector) -- switches the correction step from the reference's identity
+    preconditioner (diag_tools.py:137-139) to t = r / (diag - theta), |diag - theta| >= precond_floor * max(1, |theta|):
+    same eigenpairs, fewer cycles in cold sweeps; opt-in because the iteration counts then differ from the reference.
     ``consensus``: optional callable applied to the small device arrays right before the host reads them
     (sharded sweeps: a broadcast from rank 0, so that every rank takes the same control decisions and the
     collectives inside ``matvec`` stay matched whatever the last bit of a reduction does).
@@ -144,7 +151,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     if native is None:
         native = os.environ.get("PDMRG_PY_DAVIDSON", "0") != "1"
     if native and plan is not None and nroots <= 4 and len(x0) <= nroots and n > nroots:
-        return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats)
+        return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats,
+                               diag=diag, precond_floor=precond_floor)
     max_space = max_space + 3 * nroots
     rows = max_space + nroots
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
@@ -155,6 +163,7 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     small_tail = W.small[-8:]
     gs_norm = W.norms[-2:-1]
 
+    use_pc, pc_best, pc_stall = diag is not None, float("inf"), 0
     n_mv = 0
     space = 0
     fresh = True
@@ -200,15 +209,26 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
         # with no host round trip in between -- projection against the basis and the new norm
         for k in range(nr):
             ops.residual(v[:, k], e[k], W.XS, W.AX, space, W.R[k][:n], norm2_out=W.norms[2 * k:2 * k + 1])
+            scale = W.norms[2 * k:2 * k + 1]
+            if use_pc:                                             # la_tools.py:510 with a diagonal preconditioner
+                scale = W.norms[2 * nroots + 8 + k:2 * nroots + 9 + k]
+                ops.precond(W.R[k][:n], diag, e[k], precond_floor * max(1.0, abs(e[k])), scale)
             c = ops.dots(W.XS, space, W.R[k][:n])
-            ops.project(W.XS, space, c, W.R[k][:n], scale_dev=W.norms[2 * k:2 * k + 1],
-                        norm2_out=W.norms[2 * k + 1:2 * k + 2])
+            ops.project(W.XS, space, c, W.R[k][:n], scale_dev=scale, norm2_out=W.norms[2 * k + 1:2 * k + 2])
         if consensus is not None:
             consensus(W.norms[:2 * nr])
         nrm = W.norms[:2 * nr].cpu().numpy()                       # D2H #2 of the cycle
         dx2, px2 = nrm[0::2], nrm[1::2]
         if stats is not None:
             stats.setdefault("res_history", []).append(float(np.sqrt(dx2.max())))
+        if use_pc:
+            # safeguard (as in csrc/davidson.cu): no halving of the residual within two restart periods -> identity
+            res_now = float(np.sqrt(dx2.max()))
+            if res_now < 0.5 * pc_best:
+                pc_best, pc_stall = res_now, 0
+            else:
+                pc_stall += 1
+                use_pc = pc_stall <= 2 * max_space
         trial = []
         for k in range(nr):
             if dx2[k] > thresh2 and px2[k] > lindep:               # la_tools.py:505-537

@@ -179,6 +179,21 @@ class HeffPlan:
         self.n_apply += 1
         return y
 
+    def diag(self, sign=-1.0, out=None):
+        """Diagonal of  sign * H_eff  (pdmrg_heff_diag), for the diagonal Davidson preconditioner."""
+        P, Dl, Dr = self.P, self.Dl, self.Dr
+        if out is None:
+            out = torch.empty(self.n, dtype=self.Ls[0].dtype, device=self.Ls[0].device)
+        for m, (L, R, wc) in enumerate(zip(self.Ls, self.Rs, self._wc)):
+            wL, wR = int(L.shape[1]), int(R.shape[1])
+            W4 = wc.reshape(wL, P, wR, P)
+            Wpp = np.ascontiguousarray(np.einsum("jpop->pjo", W4))
+            Wd = torch.from_numpy(Wpp).to(L.device)
+            check(lib.pdmrg_heff_diag(self.code, P, Dl, Dr, wL, wR, _ptr(L), _ptr(R), _ptr(Wd), float(sign), int(m > 0),
+                                      _ptr(out), _stream()), "pdmrg_heff_diag")
+            self._keep = Wd                                     # alive until the kernel has run (stream-ordered free)
+        return out
+
     def apply_timed(self, x, y, sign=-1.0):
         """apply() with per-stage CUDA-event timing; returns [ms stage A, ms mix, ms stage C]."""
         ws = self.workspace.get(self.ws_bytes)
@@ -310,6 +325,13 @@ class VecOps:
         check(lib.pdmrg_vec_project(self.code, self.n, m, _ptr(X), X.stride(0), _ptr(c_dev), _ptr(scale_dev), _ptr(r),
                                     _ptr(norm2_out), _ptr(self.scratch), self.scratch.numel(), _stream()),
               "pdmrg_vec_project")
+        return norm2_out
+
+    def precond(self, r, diag, theta, floor, norm2_out):
+        """r <- r / (diag - theta) (floored); norm2_out[0] = ||r||^2 of the result."""
+        th = complex(theta)
+        check(lib.pdmrg_vec_precond(self.code, self.n, _ptr(r), _ptr(diag), th.real, th.imag, float(floor), _ptr(norm2_out),
+                                    _ptr(self.scratch), self.scratch.numel(), _stream()), "pdmrg_vec_precond")
         return norm2_out
 
     def normalize(self, src, norm2_dev, out):

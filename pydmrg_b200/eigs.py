@@ -115,7 +115,8 @@ def check_overlap(guess, vecs, E, preserveState, ctx):
 
 def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
               orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
-              fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000, shard=None, max_space=12):
+              fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000, shard=None, max_space=12,
+              precond=None, precond_floor=0.1):
     """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
     array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise.
 
@@ -123,7 +124,8 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     bonds with min(Dl, Dr) >= shard.min_dim is split over the ranks (one all-reduce of y per
     mat-vec).  The Davidson control scalars and the final eigenvectors are taken from rank 0, so the ranks
     cannot drift apart.  ``max_space``: Davidson subspace before a restart (la_tools.py:318 default 12, widened by
-    3 per root, :412); a larger one trades vector passes for fewer mat-vecs in cold sweeps."""
+    3 per root, :412); a larger one trades vector passes for fewer mat-vecs in cold sweeps.  ``precond='diag'``:
+    diagonal Davidson preconditioner built from diag(H_eff) (davidson.davidson) instead of the reference's identity."""
     ctx = ctx or default_context()
     own_plan = plan is None
     sharded = None
@@ -140,6 +142,9 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
             guesses.append(ctx.dev(mpsL[s][site]).reshape(-1))
         else:
             guesses.append(two_site_guess(ctx.dev(mpsL[s][site]), ctx.dev(mpsL[s][site + 1]), ctx).reshape(-1))
+    if precond not in (None, "diag"):
+        raise ValueError("precond must be None or 'diag'")
+    pc = dict(diag=plan.diag(-1.0), precond_floor=precond_floor) if (precond == "diag" and alg == "davidson") else {}
     if alg == "davidson" and sharded is not None:
         # identical start vectors on every rank: together with the all-reduced images and the deterministic vector
         # kernels this keeps the ranks' Krylov bases identical (a residual of norm 1e-9 that differed by 1e-13
@@ -148,14 +153,14 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
             shard.consensus(gk)
         vals, vecs = davidson(lambda x, y: sharded.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=None,
-                              native=False, max_cycle=max_cycle, consensus=shard.consensus, max_space=max_space)
+                              native=False, max_cycle=max_cycle, consensus=shard.consensus, max_space=max_space, **pc)
         E = -vals
         if stats is not None:
             stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
     elif alg == "davidson":
         vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=plan,
-                              native=native, max_cycle=max_cycle, max_space=max_space)
+                              native=native, max_cycle=max_cycle, max_space=max_space, **pc)
         E = -vals                                               # diag_tools.py:265,273
     elif alg == "exact":
         E, vecs = _eigs_exact(plan, n, nS, ctx)

@@ -136,6 +136,16 @@ class VecOps:
         norm2_out[0] = torch.linalg.vector_norm(r[:self.n]) ** 2
         return norm2_out
 
+    def precond(self, r, diag, theta, floor, norm2_out):
+        den = diag[:self.n].to(torch.complex128) - complex(theta)
+        a = den.abs()
+        unit = torch.where(a > 0, den / a.clamp_min(1e-300), torch.ones_like(den))
+        den = torch.where(a < floor, unit * floor, den)
+        t = r[:self.n] / (den if self.dt.is_complex else den.real)
+        r[:self.n] = t
+        norm2_out[0] = torch.linalg.vector_norm(t) ** 2
+        return norm2_out
+
     def normalize(self, src, norm2_dev, out):
         out[:self.n] = src[:self.n] / torch.sqrt(norm2_dev[0])
         return out
@@ -174,6 +184,16 @@ class HeffPlan:
         y.reshape(P, Dl, Dr).copy_(sign * acc)
         self.n_apply += 1
         return y
+
+    def diag(self, sign=-1.0, out=None):
+        P, Dl, Dr = self.P, self.Dl, self.Dr
+        acc = torch.zeros((P, Dl, Dr), dtype=self.ops[0][0].dtype)
+        for (L, Wc, R) in self.ops:
+            wL, wR = L.shape[1], R.shape[1]
+            W4 = torch.from_numpy(np.ascontiguousarray(Wc)).to(acc.dtype).reshape(wL, P, wR, P)
+            Wpp = torch.einsum("jpop->pjo", W4)
+            acc += torch.einsum("kjk,pjo,sos->pks", L, Wpp, R)
+        return (sign * acc).reshape(-1).contiguous()
 
     def close(self):
         pass

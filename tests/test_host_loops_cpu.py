@@ -259,3 +259,33 @@ def test_larger_davidson_subspace_needs_fewer_matvecs(monkeypatch, golden):
     dav.release_workspaces()
     assert abs(out[24][0] - out[12][0]) < 1e-7 * abs(out[12][0])
     assert out[24][1] < out[12][1]
+
+
+def test_diagonal_preconditioner_same_eigenpair_fewer_matvecs(monkeypatch, golden):
+    """davidson(diag=...): t = r / (diag(A) - theta) in the correction step.  On the reference's seeded problem the
+    eigenpair is the same (the fixed point does not depend on the preconditioner) and the mat-vec count drops; the
+    emulated diagonal equals the diagonal of the dense operator."""
+    from emu_device import install, HeffPlan, Context
+    from oracle import dmrg_oracle as orc
+    D = install(monkeypatch.setattr)
+    from pydmrg_b200 import davidson as dav
+    g = golden["davidson"]
+    L, R, W, x0 = g["L"], g["R"], g["W"], g["x0"]
+    ctx = Context("c128")
+    d, Dl, Dr = x0.shape
+    plan = HeffPlan(1, d, Dl, Dr, [(ctx.dev(L), D.combine_onesite(W, L.shape[1], R.shape[1], d, np.complex128), ctx.dev(R))], None)
+    diag = plan.diag(-1.0)
+    dense = -orc.heff_dense_onesite([L], [W], [R], x0.shape)           # matvec = -H
+    assert np.allclose(diag.numpy(), np.diag(dense), atol=1e-13 * np.abs(dense).max())
+    out = {}
+    for use in (False, True):
+        dav.release_workspaces()
+        st = {}
+        e, vecs = dav.davidson(lambda x, y: plan.apply(x, y, -1.0), [ctx.dev(x0.ravel())], x0.size, 1, torch.device("cpu"), nroots=1,
+                               stats=st, native=False, res_tol=1e-10, diag=diag if use else None)
+        out[use] = (e[0], st["n_matvec"], vecs[0].numpy())
+    dav.release_workspaces()
+    assert abs(out[True][0] - out[False][0]) < 1e-9 * abs(out[False][0])
+    assert abs(out[True][0] - g["exact_min_real"]) < 1e-9 * abs(g["exact_min_real"])
+    assert abs(abs(np.vdot(out[True][2], out[False][2])) - 1) < 1e-8
+    assert out[True][1] < out[False][1]

@@ -223,3 +223,21 @@ def test_gauge_utilities(E):
         s = np.linalg.svd(psi.reshape(2 ** (b + 1), -1), compute_uv=False)
         p = s[s > 1e-15] ** 2
         assert abs(EE[0, b] - np.sum(-p * np.log2(p))) < 1e-10
+
+
+def test_preconditioned_two_site_run(E, golden):
+    """run_dmrg(..., precond='diag'): same energy as ED / the unpreconditioned run, fewer mat-vecs from a cold start."""
+    from pydmrg_b200 import dmrg, mpo as M
+    g = golden["multistate"]
+    mpo = M.asep_mpo(8, tuple(float(v) for v in g["params"]))
+    ctx = E.Context("c128")
+    res = {}
+    for pc in (None, "diag"):
+        np.random.seed(1)
+        st = {}
+        out = dmrg.run_dmrg(mpo, mbd=16, tol=1e-10, maxIter=3, twoSite=True, ctx=ctx, native=False, res_tol=1e-10, stats=st,
+                            precond=pc)
+        res[pc] = (out[0], st["n_matvec"])
+    ed = g["asep8_ed"][0]
+    assert abs(res["diag"][0] - ed) < 1e-9 * abs(ed) and abs(res[None][0] - ed) < 1e-9 * abs(ed)
+    assert res["diag"][1] < res[None][1]

@@ -16,6 +16,19 @@ one)
   PDMRG_RUN_PENDING=1 timeout 300 python -m pytest tests/test_pending_gpu.py -m gpu -q > gpurun_out/r2_pending.log 2>&1; echo "pending rc=$?" | tee -a gpurun_out/r2_pending.log
   # (b) bench line with the start policy of the warm-started truncation in place (profiles/README note)
   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_err.log; echo "bench rc=$?"
+  # (b2) cold scan point with fewer Davidson cycles: diagonal preconditioner and a larger subspace
+  timeout 300 python - > gpurun_out/r2_scan_precond.txt 2>&1 <<'PY'
+import time, numpy as np, torch
+from pydmrg_b200 import mpo as M, scan
+mpo_of = lambda s: M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+scan.run_scan(mpo_of, [-0.5], 64, maxIter=0)                                     # start-up
+for opts in ({}, {"precond": "diag"}, {"max_space": 24}, {"precond": "diag", "max_space": 24}):
+    st = {}
+    np.random.seed(0); torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = scan.run_scan(mpo_of, [-0.5, 0.17], 256, maxIter=3, stats=st, **opts)
+    torch.cuda.synchronize()
+    print(opts, "sec/point", r["sec"], "E", [complex(e) for e in r["E"]], "matvecs", st.get("n_matvec"), "cycles", st.get("cycles"), flush=True)
+PY
   # (c) where does a latency-bound Davidson cycle go (host vs device), one process
   timeout 200 python tools/scan_contention.py > gpurun_out/r2_contention_n1.txt 2>&1
   ;;
