@@ -136,3 +136,27 @@ def test_recycle_window_bookkeeping():
     assert not truncate.recycle_allowed(cache, 7, (2048, 2048, 512))      # the bond changed shape: start over
     truncate.note_exact_visit(cache, 8, (512, 512, 256), 1e-20)
     assert truncate.recycle_allowed(cache, 8, (512, 512, 256))
+
+
+def test_new_entry_points_marshal_and_validate_without_gpu(lib):
+    """The ctypes signatures of the entry points added for sharded sweeps and the preconditioner match the library
+    (a wrong arity / type raises in ctypes), and their host-side argument checks answer before any launch."""
+    import ctypes
+    L = lib.lib
+    e_host = (ctypes.c_double * 2)()
+    n_mv, cyc, last = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+    args = (None, None, None, -1.0, 1, 8, None, 8, 1, 1, 12, 1e-14, -1.0, 10, 0, None, None, None, 8, None, 0, None, 0,
+            e_host, None, 8, ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), None)
+    assert L.pdmrg_davidson(*args) != 0 and b"null plan" in L.pdmrg_last_error()
+    assert L.pdmrg_davidson_precond(*args, None, 0.1) != 0 and b"diagonal" in L.pdmrg_last_error()
+    rc = L.pdmrg_env_update_right_cols(1, 2, 8, 8, 3, 3, None, None, None, None, 6, 4, None, None, 0, None)
+    assert rc != 0 and b"ket range" in L.pdmrg_last_error()
+    rc = L.pdmrg_env_update_left_cols(7, 2, 8, 8, 3, 3, None, None, None, None, 0, 4, None, None, 0, None)
+    assert rc != 0 and b"dtype" in L.pdmrg_last_error()
+    rc = L.pdmrg_env_update_right_cols(1, 2, 8, 8, 3, 3, None, None, None, None, 0, 8, None, None, 0, None)
+    assert rc != 0 and b"workspace too small" in L.pdmrg_last_error()
+    rc = L.pdmrg_vec_precond(1, 16, None, None, 0.0, 0.0, 0.0, None, None, 1 << 24, None)
+    assert rc != 0 and b"floor" in L.pdmrg_last_error()
+    rc = L.pdmrg_heff_diag(5, 4, 8, 8, 3, 3, None, None, None, -1.0, 0, None, None)
+    assert rc != 0 and b"dtype" in L.pdmrg_last_error()
+    assert L.pdmrg_launch_count() == 0
