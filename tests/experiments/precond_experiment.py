@@ -11,10 +11,12 @@ i.e. the cold sweeps that dominate a scan point need 1.6-1.9x fewer cycles; ener
 diag(H_eff)[p1,p2,k,s] = sum_{j,o} L[k,j,k] (sum_l W1[j,l,p1,p1] W2[l,o,p2,p2]) R[s,o,s] is an O(d^2 w^2 chi^2) kernel.
 Not in the product yet (needs a device kernel for the diagonal and the division).
 
-    python tools/precond_experiment.py
+    python tests/experiments/precond_experiment.py
+
+(lives under tests/ because it runs on the oracle, which only test code may import)
 """
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.linalg as sla
 from oracle import dmrg_oracle as orc
 from pydmrg_b200 import mpo as M
