@@ -84,6 +84,8 @@ def main():
     ap.add_argument("--max-iter", type=int, default=4)
     ap.add_argument("--pin-cores", action="store_true",
                     help="give every local rank its own slice of the host cores (the scan is host-latency bound)")
+    ap.add_argument("--precond", default=None, choices=[None, "diag"], help="Davidson preconditioner (default: the reference's identity)")
+    ap.add_argument("--max-space", type=int, default=12, help="Davidson subspace before a restart (reference: 12)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.pin_cores and hasattr(os, "sched_setaffinity"):
@@ -102,16 +104,24 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter)
+    stats = {}
+    res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter, stats=stats,
+                   precond=args.precond, max_space=args.max_space)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    per_rank = [{"rank": rank, "sec": round(sum(res["sec"]), 3), "points": len(res["points"]), "cycles": stats.get("cycles"),
+                 "n_matvec": stats.get("n_matvec")}]
     if world > 1:
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
     if rank == 0:
         print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
                           "host_cores": os.cpu_count(), "cores_per_rank": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
-                          "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt,
+                          "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt, "per_rank": per_rank,
+                          "precond": args.precond, "max_space": args.max_space,
                           "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
     if world > 1:
         dist.destroy_process_group()
