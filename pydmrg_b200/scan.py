@@ -94,6 +94,18 @@ def main():
         per = max(1, len(cores) // max(1, lw))
         mine = cores[lr * per:(lr + 1) * per] or cores
         os.sched_setaffinity(0, set(mine))
+    blas_threads = None
+    if world > 1:
+        # NumPy / SciPy BLAS pools default to ALL host cores in every rank and their idle workers spin before they
+        # sleep: eight ranks of a latency-bound scan would oversubscribe the host.  Give each rank its share.
+        try:
+            import scipy.linalg  # noqa: F401  (load SciPy's BLAS too: only loaded pools can be limited)
+            from threadpoolctl import threadpool_limits
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            blas_threads = max(1, (os.cpu_count() or 1) // max(1, lw))
+            threadpool_limits(limits=blas_threads)
+        except Exception:
+            blas_threads = None
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     if world > 1:
         dist.init_process_group("nccl")
@@ -121,7 +133,7 @@ def main():
         print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
                           "host_cores": os.cpu_count(), "cores_per_rank": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
                           "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt, "per_rank": per_rank,
-                          "precond": args.precond, "max_space": args.max_space,
+                          "precond": args.precond, "max_space": args.max_space, "blas_threads_per_rank": blas_threads,
                           "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
     if world > 1:
         dist.destroy_process_group()

@@ -42,9 +42,9 @@ two)
 eight)
   # host contention of the latency-bound scan: cycles/s per rank with 1, 2, 4, 8 ranks, unpinned and pinned
   for n in 1 2 4 8; do
-    for pin in "" "--pin"; do
+    for opt in "" "--pin" "--blas1"; do
       timeout 200 python -m torch.distributed.run --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n \
-          tools/scan_contention.py $pin > gpurun_out/r2_contention_n${n}${pin:+_pin}.txt 2>&1
+          tools/scan_contention.py $opt > gpurun_out/r2_contention_n${n}${opt:+_${opt#--}}.txt 2>&1
     done
   done
   nproc > gpurun_out/r2_host.txt; lscpu >> gpurun_out/r2_host.txt 2>&1; cat /sys/fs/cgroup/cpu.max >> gpurun_out/r2_host.txt 2>&1

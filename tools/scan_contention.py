@@ -3,7 +3,7 @@ every rank runs the same small-chi Davidson-heavy stage on its own GPU and repor
 second, the host core count and its affinity.  If cycles/s per rank drops as ranks are added, the ranks are
 starving each other on the host (the 8-GPU scan of round 1 ran 4.7x slower per point than one process alone).
 
-    python -m torch.distributed.run --nproc-per-node 8 tools/scan_contention.py [--pin]
+    python -m torch.distributed.run --nproc-per-node 8 tools/scan_contention.py [--pin] [--blas1]
 """
 import os, sys, time
 import numpy as np, torch
@@ -13,6 +13,10 @@ lr, lw = int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("LOCAL_WORLD_S
 if "--pin" in sys.argv and hasattr(os, "sched_setaffinity"):
     cores = sorted(os.sched_getaffinity(0)); per = max(1, len(cores) // lw)
     os.sched_setaffinity(0, set(cores[lr * per:(lr + 1) * per] or cores))
+if "--blas1" in sys.argv:                       # hypothesis: spinning BLAS worker pools (one per rank, all cores each)
+    import scipy.linalg  # noqa: F401  (only loaded pools can be limited)
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=1)
 torch.cuda.set_device(lr)
 from pydmrg_b200 import dmrg, mpo as M
 mpo = M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))
