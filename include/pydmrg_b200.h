@@ -231,7 +231,8 @@ int pdmrg_davidson(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const 
                    int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream);
 /* The same loop with a diagonal preconditioner in the correction step (opt-in: iteration counts then differ from
  * the reference, whose preconditioner is the identity, tools/diag_tools.py:137-139; it acts at la_tools.py:510):
- *   t = r / (diag - theta),  |diag_i - theta| kept >= pc_floor * max(1, |theta|),
+ *   t = r / (diag - theta),  |diag_i - theta| kept >= pc_floor (absolute, in units of the operator: the spacing of the
+ *   diagonal is set by the local couplings, not by the total eigenvalue, which grows with the chain length),
  * `diag` = diagonal of the operator sign * H_eff (n elements of dtype, e.g. from pdmrg_heff_diag with the same sign).
  * Safeguard: if the residual is not halved within two restart periods the loop continues with the identity. */
 int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs, double sign,

@@ -317,8 +317,7 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
       const double* scale_slot = norms + 2 * k;                       // ||r||^2: the projected direction starts from r / ||r||
       if (use_pc) {                                                       // ... or from t / ||t||, t = r / (diag - theta)
         double* tn = norms + 2 * nroots + 8 + k;
-        if (pdmrg_vec_precond(dtype, n, rv(k), diag, e[k].real(), e[k].imag(), pc_floor * std::max(1.0, std::abs(e[k])), tn,
-                              vscratch, vsb, stream)) return 1;
+        if (pdmrg_vec_precond(dtype, n, rv(k), diag, e[k].real(), e[k].imag(), pc_floor, tn, vscratch, vsb, stream)) return 1;
         scale_slot = tn;
       }
       double* cdev = small + (size_t)E * (2 * rows * (nroots + 2));

@@ -139,7 +139,7 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     When the H_eff ``plan`` is given the loop runs in C++ (``pdmrg_davidson``) unless
     ``native=False`` / PDMRG_PY_DAVIDSON=1; this Python loop is the specification it mirrors.
     ``diag``: diagonal of the operator (device vector) -- switches the correction step from the reference's identity
-    preconditioner (diag_tools.py:137-139) to t = r / (diag - theta), |diag - theta| >= precond_floor * max(1, |theta|):
+    preconditioner (diag_tools.py:137-139) to t = r / (diag - theta), |diag - theta| >= precond_floor (absolute):
     same eigenpairs, fewer cycles in cold sweeps; opt-in because the iteration counts then differ from the reference.
     ``consensus``: optional callable applied to the small device arrays right before the host reads them
     (sharded sweeps: a broadcast from rank 0, so that every rank takes the same control decisions and the
@@ -212,7 +212,7 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
             scale = W.norms[2 * k:2 * k + 1]
             if use_pc:                                             # la_tools.py:510 with a diagonal preconditioner
                 scale = W.norms[2 * nroots + 8 + k:2 * nroots + 9 + k]
-                ops.precond(W.R[k][:n], diag, e[k], precond_floor * max(1.0, abs(e[k])), scale)
+                ops.precond(W.R[k][:n], diag, e[k], precond_floor, scale)
             c = ops.dots(W.XS, space, W.R[k][:n])
             ops.project(W.XS, space, c, W.R[k][:n], scale_dev=scale, norm2_out=W.norms[2 * k + 1:2 * k + 2])
         if consensus is not None:
