@@ -156,3 +156,65 @@ def test_shard_spec_env_update_sums_to_the_full_block(monkeypatch):
             acc = acc + parallel.ShardSpec(rank, 3, Dist(), min_dim=16).env_update(direction, A, W, blk, Ctx()).numpy()
         f = orc.env_update_right if direction == "right" else orc.env_update_left
         assert np.allclose(acc, f(A.numpy(), W, blk.numpy(), None, "blas"), atol=1e-12)
+
+
+# ---- the .cu file itself, compiled with g++ against host stand-ins for the kernels it launches ----------------------
+@pytest.fixture(scope="module")
+def env_cols_host(tmp_path_factory):
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = str(tmp_path_factory.mktemp("env_cols_host") / "libenv_cols_host.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-w", "-include", "cmath",
+                    "-I/usr/local/cuda/include", "-x", "c++", os.path.join(root, "pydmrg_b200", "csrc", "env_cols.cu"),
+                    os.path.join(root, "tests", "native_host", "env_cols_host_shim.cpp"), "-o", out], check=True)
+    lib = ctypes.CDLL(out)
+    lib.shim_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+@pytest.mark.parametrize("use_W,use_bra", [(True, False), (True, True), (False, False)])
+@pytest.mark.parametrize("dims", [(2, 6, 9), (2, 8, 8), (3, 5, 4)])
+def test_env_cols_cu_on_host_memory(env_cols_host, dims, use_W, use_bra, dtype):
+    """pydmrg_b200/csrc/env_cols.cu executed as it is (host stand-ins for permute / GEMM / mix): the column slices
+    written in place assemble the oracle's full block update, and nothing outside the owned columns is touched."""
+    import ctypes
+    lib = env_cols_host
+    d, Dl, Dr = dims
+    rng = np.random.default_rng(7 * d + Dl + 3 * Dr)
+    cplx = dtype == "c128"
+    dt = np.complex128 if cplx else np.float64
+    rnd = (lambda *s: crand(rng, *s)) if cplx else (lambda *s: rng.standard_normal(s))
+    wl, wr = (4, 3) if use_W else (3, 3)
+    A = np.ascontiguousarray(rnd(d, Dl, Dr))
+    bra = np.ascontiguousarray(rnd(d, Dl, Dr)) if use_bra else None
+    P = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+    ws = np.zeros(1 << 20, np.uint8)
+    for direction in ("right", "left"):
+        W = np.ascontiguousarray(rnd(wl, wr, d, d) * (rng.random((wl, wr, 1, 1)) > 0.4)).astype(dt) if use_W else None
+        if direction == "right":
+            blk = np.ascontiguousarray(rnd(Dl, wl, Dl)); n, w_out = Dr, wr
+            full = orc.env_update_right(A, W, blk, bra, "blas")
+            fn = lib.pdmrg_env_update_right_cols
+        else:
+            blk = np.ascontiguousarray(rnd(Dr, wr, Dr)); n, w_out = Dl, wl
+            full = orc.env_update_left(A, W, blk, bra, "blas")
+            fn = lib.pdmrg_env_update_left_cols
+        out = np.full((n, w_out, n), np.nan, dt)
+        cuts = [0, n // 3, n // 3, n]
+        for k0, k1 in zip(cuts[:-1], cuts[1:]):
+            before = out.copy()
+            rc = fn(1 if cplx else 0, d, Dl, Dr, wl, wr, P(W), P(blk), P(A), P(bra), k0, k1 - k0, P(out), P(ws),
+                    ctypes.c_size_t(ws.size), None)
+            assert rc == 0, lib.shim_last_error()
+            untouched = np.ones(out.shape, bool); untouched[:, :, k0:k1] = False
+            assert np.array_equal(np.isnan(out[untouched]), np.isnan(before[untouched]))
+            same = ~np.isnan(before) & untouched
+            assert np.array_equal(out[same], before[same])
+        assert not np.isnan(out).any()
+        assert np.allclose(out, full, rtol=0, atol=1e-12 * np.abs(full).max())
