@@ -171,7 +171,7 @@ def env_cols_host(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("env_cols_host") / "libenv_cols_host.so")
     subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-w", "-include", "cmath",
                     "-I/usr/local/cuda/include", "-x", "c++", os.path.join(root, "pydmrg_b200", "csrc", "env_cols.cu"),
-                    os.path.join(root, "tests", "native_host", "env_cols_host_shim.cpp"), "-o", out], check=True)
+                    os.path.join(root, "tests", "native_host", "kernels_host_shim.cpp"), "-o", out], check=True)
     lib = ctypes.CDLL(out)
     lib.shim_last_error.restype = ctypes.c_char_p
     return lib
