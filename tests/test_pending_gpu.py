@@ -190,3 +190,25 @@ def test_diagonal_preconditioner_kernels_and_loops(P, dtype):
     for key, (e, nmv) in res.items():
         assert abs(e - ref) < 1e-9 * abs(ref), key
     assert res[(False, True)][1] < res[(False, False)][1] and res[(True, True)][1] < res[(True, False)][1]
+
+
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+@pytest.mark.parametrize("m", [0, 5, 16, 17, 18, 28, 40])
+def test_project_with_more_than_sixteen_vectors(P, dtype, m):
+    """pdmrg_vec_project in passes of 16 basis vectors (subspaces of nroots >= 2 or max_space > 12):
+    r <- (r - sum_i c_i X_i) / sqrt(scale), norm2 = ||r||^2 of the result."""
+    import torch
+    from pydmrg_b200 import device as D
+    c = P.core.Context(dtype)
+    n = 3001
+    rng = np.random.default_rng(m)
+    rnd = (lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)) if dtype == "c128" else (lambda *s: rng.standard_normal(s))
+    X, r, cf = rnd(max(m, 1), n), rnd(n), rnd(max(m, 1))
+    ops = D.VecOps(c.code, n, c.device)
+    Xd, rd, cd_ = c.dev(X), c.dev(r), c.dev(cf)
+    scale = torch.tensor([2.5], dtype=torch.float64, device=c.device)
+    n2 = torch.zeros(1, dtype=torch.float64, device=c.device)
+    ops.project(Xd, m, cd_, rd, scale_dev=scale, norm2_out=n2)
+    ref = (r - (cf[:m] @ X[:m] if m else 0)) / np.sqrt(2.5)
+    assert np.max(np.abs(c.host(rd) - ref)) < 1e-12 * np.abs(ref).max()
+    assert abs(n2.item() - np.linalg.norm(ref) ** 2) < 1e-11 * np.linalg.norm(ref) ** 2
