@@ -341,3 +341,22 @@ def test_periodic_chain(E):
         np.random.seed(2)
         out = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=6, ctx=ctx, native=False, res_tol=1e-11, twoSite=two)
         assert abs(out[0] - top) < 1e-8 * max(1.0, abs(top)), (two, out[0], top)
+
+
+def test_two_site_run_with_warm_started_truncation(E):
+    """run_dmrg(twoSite=True) at chi = 64 on 16 sites -- the 128 x 128 cuts take the projective route and, under the
+    start policy, the warm-started one -- against the same run with ``recycle=False``: the whole host flow
+    (sweeps, Python Davidson loop, truncation bookkeeping) with nothing stubbed above the device entry points."""
+    from pydmrg_b200 import dmrg, mpo as M
+    ctx = E.Context("c128")
+    mpo = M.heisenberg_mpo(16)
+    res = {}
+    for rec in (False, True):
+        np.random.seed(2)
+        st = {}
+        out = dmrg.run_dmrg(mpo, mbd=64, tol=0.0, maxIter=3, twoSite=True, ctx=ctx, native=False, res_tol=1e-10, stats=st, recycle=rec)
+        res[rec] = (out[0], out[1], st)
+    assert res[True][2].get("n_recycled", 0) > 0 and res[False][2].get("n_recycled", 0) == 0
+    assert res[True][2].get("n_exact_trunc", 0) >= 8                      # centre bond: both directions, every sweep
+    assert abs(res[True][0] - res[False][0]) < 1e-10 * abs(res[False][0])
+    assert abs(res[True][1] - res[False][1]) < 1e-8
