@@ -304,7 +304,7 @@ def test_two_states_options(E, golden):
         out = dmrg.run_dmrg(mpo, orthonormalize=orth, **kw)
         assert abs(out[0] - ed[0]) < 1e-7 * abs(ed[0]) and abs(out[2] - (ed[0] - ed[1])) < 1e-6
     # preserveState keeps the previous tensor whenever no eigenvector overlaps it by 0.98 (diag_tools.py:93-97).  With
-    # two states the reference then indexes a second vector that no longer exists (IndexError, dmrg.py:86); with one
+    # two states the reference then indexes a second vector that no longer exists (IndexError, dmrg.py:288); with one
     # state it runs -- reference value for this seed: E = 0.8905626478 (run here through oracle/ref_loader.py)
     np.random.seed(6)
     out = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=5, nStates=1, preserveState=True, ctx=ctx, native=False)
