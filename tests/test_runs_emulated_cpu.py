@@ -360,3 +360,37 @@ def test_two_site_run_with_warm_started_truncation(E):
     assert res[True][2].get("n_exact_trunc", 0) >= 8                      # centre bond: both directions, every sweep
     assert abs(res[True][0] - res[False][0]) < 1e-10 * abs(res[False][0])
     assert abs(res[True][1] - res[False][1]) < 1e-8
+
+
+@pytest.mark.parametrize("N", [3, 4, 5, 7])
+def test_short_and_odd_chains(E, N):
+    """Edge cases of the chain length (odd N has its own branch in the reference's allocation code,
+    mps_tools.py:217, env_tools.py:19): one-site and two-site runs against dense diagonalisation."""
+    from pydmrg_b200 import dmrg, mpo as M
+    ctx = E.Context("c128")
+    mpo = M.asep_mpo(N, PRM)
+    T = mpo[0][0][0]
+    for W in mpo[0][1:]:
+        T = np.einsum("a...,abij->b...ij", T, W)
+    idx = list(range(0, 2 * N, 2)) + list(range(1, 2 * N, 2))
+    ev = np.linalg.eigvals(T[0].transpose(idx).reshape(2 ** N, 2 ** N))
+    top = ev[np.argmax(ev.real)]
+    for two in (False, True):
+        np.random.seed(1)
+        out = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=4, ctx=ctx, native=False, res_tol=1e-11, twoSite=two)
+        assert abs(out[0] - top) < 1e-10 * abs(top)
+
+
+def test_two_site_chain_of_two_sites(E):
+    """N = 2: one bond.  Two-site sweeps solve it exactly; the reference's one-site driver cannot run it (its default
+    gaugeSiteSave = N/2 + 1 = 2 steps past the last site, dmrg.py:326 -> IndexError), and neither does this one."""
+    from pydmrg_b200 import dmrg, mpo as M
+    ctx = E.Context("c128")
+    mpo = M.asep_mpo(2, PRM)
+    T = np.einsum("abij,bckl->acikjl", mpo[0][0], mpo[0][1])[0, 0].reshape(4, 4)
+    ev = np.linalg.eigvals(T)
+    np.random.seed(1)
+    out = dmrg.run_dmrg(mpo, mbd=4, tol=1e-10, maxIter=2, ctx=ctx, native=False, res_tol=1e-11, twoSite=True)
+    assert abs(out[0] - ev[np.argmax(ev.real)]) < 1e-12
+    with pytest.raises(IndexError):
+        dmrg.run_dmrg(mpo, mbd=4, tol=1e-10, maxIter=2, ctx=ctx, native=False)
