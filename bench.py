@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip bond-step / cpu-baseline extras")
     ap.add_argument("--no-full-sweep", action="store_true", help="skip the measured two-site sweeps of the N=100 chain (~1 min)")
     ap.add_argument("--svd", default="auto", choices=["auto", "gesvd", "gesvdj", "gram"])
+    ap.add_argument("--sharded-sweep", action="store_true",
+                    help="N > 1: also time two-site sweeps of the N=100 chain with the mat-vecs and block updates of the large "
+                         "bonds sharded over the ranks (run_dmrg(shard=...)); off by default until validated on GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -362,6 +365,12 @@ def main():
                                                      "partial y over NVLink, then a flag-guarded reduce + all-gather kernel (no NCCL)"}
         fk.close()
 
+    if world > 1 and args.sharded_sweep:
+        spec = parallel.ShardSpec(rank, world, dist, mode="ket")
+        line["sweep_sec_sharded"] = full_sweep(args, ctx, shard=spec)
+        line["sweep_sec_sharded"]["how"] += "; every rank runs the sweep, mat-vecs and block updates of bonds >= %d split %d ways" % (
+            spec.min_dim, world)
+
     # ---- extras on rank 0 at N=1: bond step, sweep estimate, CPU baseline ----------------------
     if world == 1 and not args.no_extras:
         line["bond_step"] = bond_step(args, ctx, plan, L, R, W1, W2, chi)
@@ -558,7 +567,7 @@ def scan_sample():
             "E": [float(np.real(e)) for e in res["E"]], "E_imag_max": float(np.max(np.abs(np.imag(res["E"]))))}
 
 
-def full_sweep(args, ctx):
+def full_sweep(args, ctx, shard=None):
     """Measured two-site sweeps (right + left over all 99 bonds) of the TASEP N=100 chain at chi: the state is
     grown through a [16, 64, 256] chi ramp (so it is physical) and then swept five times with mbd = chi.  Two-site
     sweeps are not zero-padded: every bond grows by up to a factor d per visit, so the first two sweeps run on
@@ -574,7 +583,8 @@ def full_sweep(args, ctx):
     tmp = tempfile.mkdtemp()
     sched = [c for c in (16, 64, 256) if c < chi]
     t0 = time.perf_counter()
-    dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=True, ctx=ctx)
+    extra = {} if shard is None else {"shard": shard}
+    dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=True, ctx=ctx, **extra)
     mpsL, _ = mps_tools.load_mps(os.path.join(tmp, "st_mbd%d" % (len(sched) - 1)))
     mpsL = [[ctx.dev(t) for t in mpsL[0]]]
     F = env.calc_env(mpsL[0], mpo, chi, gaugeSite=0, ctx=ctx)
@@ -584,12 +594,13 @@ def full_sweep(args, ctx):
     for _ in range(5):
         stats = {}
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, recycle=cache)
+        E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, recycle=cache, **extra)
         torch.cuda.synchronize(); secs.append(time.perf_counter() - t0)
         bonds.append(int(max(t.shape[2] for t in mpsL[0])))
     return {"value": secs[-1], "unit": "s", "sweeps_sec": secs, "max_bond_after_sweep": bonds, "ramp_sec": ramp,
             "E": [float(np.real(E)), float(np.imag(E))], "EE": float(EE), "n_matvec": stats.get("n_matvec"),
             "bonds": 2 * (N - 1), "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0),
+            "n_sharded_solves": stats.get("n_sharded_solves", 0), "n_sharded_env": stats.get("n_sharded_env", 0),
             "how": "measured: TASEP N=%d chi=%d c128 two-site sweeps after a %s ramp" % (N, chi, sched)}
 
 

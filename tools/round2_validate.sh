@@ -38,6 +38,9 @@ two)
       tests/mgpu_sharded_sweep_check.py > gpurun_out/r2_sharded_sweep_n2.txt 2>&1; echo "sharded sweep check rc=$?"
   PDMRG_CHECK_TIMING=1 timeout 400 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 \
       tests/mgpu_sharded_sweep_check.py > gpurun_out/r2_sharded_sweep_timing_n2.txt 2>&1; echo "timing rc=$?"
+  # the same through bench.py (adds sweep_sec_sharded to the JSON line)
+  timeout 600 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 \
+      bench.py --gpus 2 --steps 5 --warmup 3 --sharded-sweep > gpurun_out/r2_bench_n2_sharded_sweep.json 2> gpurun_out/r2_bench_n2_err.log; echo "bench sharded sweep rc=$?"
   ;;
 eight)
   # host contention of the latency-bound scan: cycles/s per rank with 1, 2, 4, 8 ranks, unpinned and pinned
