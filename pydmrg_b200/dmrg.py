@@ -99,6 +99,19 @@ def renormalizeL(mpsL, v, site, nStates=1, targetState=0, ctx=None, fast=False):
     return mpsL, EE, EEs
 
 
+def _merge_stats(stats, loc):
+    """Add the counters of one local solve to the caller's statistics."""
+    if stats is None:
+        return
+    for key, val in loc.items():
+        if key == "last_residual":
+            stats[key] = val
+        elif isinstance(val, list):
+            stats.setdefault(key, []).extend(val)
+        else:
+            stats[key] = stats.get(key, 0) + val
+
+
 # ---------------------------------------------------------------------------------------
 # steps (the drop-in seam)
 # ---------------------------------------------------------------------------------------
@@ -130,8 +143,14 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
     """Two-site bond step on (site, site+1): two-site local solve (tools/diag_tools.py:146-162,
     guess :257), SVD truncation to ``mbd`` (tools/mps_tools.py:98-120), block update
     (tools/env_tools.py:40-50 / 28-38).  The singular values go to the new centre site.
-    Returns (E, mpsL, F, EE, EEs, S)."""
+    Returns (E, mpsL, F, EE, EEs, S).
+
+    ``gauge_shortcut=True`` (solver option, off by default): a bond whose local solve stops in its first cycle -- the
+    state did not change, the normal case in the last sweeps of a run -- is re-gauged from its centre tensor (one
+    ordered QR) instead of being truncated again; the centre bond, whose spectrum is reported, never takes it."""
     ctx = ctx or default_context()
+    solver = dict(solver)
+    shortcut = bool(solver.pop("gauge_shortcut", False))
     proto = mpsL[0][site]
     d1, Dl, _ = proto.shape
     d2, _, Dr = mpsL[0][site + 1].shape
@@ -153,12 +172,32 @@ def twoSiteStep(mpsL, W, F, site, direction, mbd, nStates=1, alg="davidson", ctx
             mpsL[s][site + 1] = like(Bs[min(s, n_avg - 1)], proto)
         A, B = As[0], Bs[0]
     else:
+        loc = {}
         E, v, _ = calc_eigs(mpsL, W, F, site, 1, alg=alg, oneSite=False, edgePreserveState=False, ctx=ctx,
-                            stats=stats, return_device=True, **solver)
+                            stats=loc, return_device=True, **solver)
+        _merge_stats(stats, loc)
         tick.lap(stats, "t_eig")
-        psi = v[:, 0].contiguous()
-        A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction, recycle=recycle, site=site,
-                                            warm=(mpsL[0][site], mpsL[0][site + 1]), exact=exact_trunc, stats=stats)
+        kmid = mpsL[0][site].shape[2]
+        if shortcut and not exact_trunc and alg == "davidson" and loc.get("cycles") == 1 and kmid <= mbd:
+            # The solver stopped in its first cycle: the Ritz vector IS the (normalised) guess A_c . B, whose Schmidt
+            # decomposition across this bond follows from the centre tensor alone -- a gauge move (ordered QR of a
+            # (d*D, k) matrix, the one-site renormalisation of dmrg.py:49-136 without a spectrum) instead of the
+            # truncation of the (d*Dl, d*Dr) wave-function.  Same state, same blocks up to the bond gauge.
+            if direction == "right":
+                A, nxt, EE, EEs = rdm_renormalize_right([ctx.dev(mpsL[0][site]).reshape(-1)], (d1, Dl, kmid),
+                                                        [ctx.dev(mpsL[0][site + 1])], ctx, 1, fast=True)
+                B = nxt[0]
+            else:
+                B, prv, EE, EEs = rdm_renormalize_left([ctx.dev(mpsL[0][site + 1]).reshape(-1)], (d2, kmid, Dr),
+                                                       [ctx.dev(mpsL[0][site])], ctx, 1, fast=True)
+                A = prv[0]
+            S = None
+            if stats is not None:
+                stats["n_gauge_moves"] = stats.get("n_gauge_moves", 0) + 1
+        else:
+            psi = v[:, 0].contiguous()
+            A, B, S, EE, EEs = truncate_twosite(psi, (d1, d2, Dl, Dr), mbd, ctx, direction, recycle=recycle, site=site,
+                                                warm=(mpsL[0][site], mpsL[0][site + 1]), exact=exact_trunc, stats=stats)
         tick.lap(stats, "t_svd")
         mpsL[0][site] = like(A, proto)
         mpsL[0][site + 1] = like(B, proto)
@@ -279,6 +318,7 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
     ``recycle``: two-site sweeps after the first reuse each bond's previous singular bases
     (truncate.truncate_twosite); False decomposes every bond from scratch."""
     ctx = ctx or default_context()
+    shortcut = bool(solver.pop("gauge_shortcut", False))         # two-site only (twoSiteStep)
     host_in = not is_dev(mpsL[0][0])
     mpsL = [[ctx.dev(t) for t in M] for M in mpsL]
     F = [[ctx.dev(t) for t in Fm] for Fm in F]
@@ -301,7 +341,7 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
         cache = {} if (recycle and nStates == 1) else None      # the warm-started truncation follows ONE state
         while cont:
             E, mpsL, F, EE, EEs, S = twoSiteSweep(mpsL, W, F, mbd, alg=alg, ctx=ctx, stats=stats, recycle=cache,
-                                                  nStates=nStates, **solver)
+                                                  nStates=nStates, gauge_shortcut=shortcut, **solver)
             cont, conv, E_prev, iterCnt = checkConv(E_prev, E, tol, iterCnt, maxIter, minIter, nStates=nStates,
                                                     targetState=targetState)
         gaugeSiteSave = 0      # after a left sweep the centre is on site 0

@@ -394,3 +394,25 @@ def test_two_site_chain_of_two_sites(E):
     assert abs(out[0] - ev[np.argmax(ev.real)]) < 1e-12
     with pytest.raises(IndexError):
         dmrg.run_dmrg(mpo, mbd=4, tol=1e-10, maxIter=2, ctx=ctx, native=False)
+
+
+def test_gauge_shortcut_for_unchanged_bonds(E):
+    """run_dmrg(twoSite=True, gauge_shortcut=True): bonds whose local solve stops in its first cycle are re-gauged from
+    the centre tensor instead of truncated again -- same energies, entropy and mat-vec count as the plain run."""
+    from pydmrg_b200 import dmrg, mpo as M
+    ctx = E.Context("c128")
+    mpo = M.asep_mpo(14, PRM)
+    res = {}
+    for gs in (False, True):
+        np.random.seed(2)
+        st = {}
+        out = dmrg.run_dmrg(mpo, mbd=32, tol=0.0, maxIter=6, twoSite=True, ctx=ctx, native=False, res_tol=1e-9, stats=st,
+                            gauge_shortcut=gs)
+        res[gs] = (out[0], out[1], st)
+    assert res[True][2].get("n_gauge_moves", 0) > 50 and res[False][2].get("n_gauge_moves", 0) == 0
+    assert abs(res[True][0] - res[False][0]) < 1e-11 * abs(res[False][0])
+    assert abs(res[True][1] - res[False][1]) < 1e-9
+    assert abs(res[True][2]["n_matvec"] - res[False][2]["n_matvec"]) <= 0.02 * res[False][2]["n_matvec"]
+    # one-site sweeps ignore the option
+    np.random.seed(2)
+    dmrg.run_dmrg(mpo, mbd=8, tol=1e-6, maxIter=1, ctx=ctx, native=False, gauge_shortcut=True)

@@ -29,6 +29,28 @@ for opts in ({}, {"precond": "diag"}, {"max_space": 24}, {"precond": "diag", "ma
     torch.cuda.synchronize()
     print(opts, "sec/point", r["sec"], "E", [complex(e) for e in r["E"]], "matvecs", st.get("n_matvec"), "cycles", st.get("cycles"), flush=True)
 PY
+  # (b3) converged chi=1024 sweeps with and without the gauge shortcut
+  timeout 400 python - > gpurun_out/r2_gauge_shortcut.txt 2>&1 <<'PY'
+import time, numpy as np, torch
+from pydmrg_b200 import core, dmrg, env, mpo as M
+ctx = core.Context("c128")
+mpo = M.asep_mpo(100, (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, -0.5))
+np.random.seed(0)
+out = dmrg.run_dmrg(mpo, mbd=[16, 64, 256], tol=1e-9, maxIter=1, twoSite=True, ctx=ctx, returnState=True)
+for gs in (False, True):
+    mpsL = [[ctx.dev(t) for t in out[-1][0]]]
+    F = env.calc_env(mpsL[0], mpo, 1024, gaugeSite=0, ctx=ctx)
+    cache = {}
+    for sw in range(6):
+        st = {}
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, 1024, ctx=ctx, stats=st, recycle=cache, gauge_shortcut=gs)
+        torch.cuda.synchronize()
+        print("gauge_shortcut", gs, "sweep", sw, "%.3f s" % (time.perf_counter() - t0), "E", complex(E), "EE", float(EE),
+              {k: st.get(k) for k in ("n_matvec", "n_gauge_moves", "n_recycled", "n_exact_trunc")}, flush=True)
+    del mpsL, F, cache
+    torch.cuda.empty_cache()
+PY
   # (c) where does a latency-bound Davidson cycle go (host vs device), one process
   timeout 200 python tools/scan_contention.py > gpurun_out/r2_contention_n1.txt 2>&1
   ;;
