@@ -212,3 +212,27 @@ def test_project_with_more_than_sixteen_vectors(P, dtype, m):
     ref = (r - (cf[:m] @ X[:m] if m else 0)) / np.sqrt(2.5)
     assert np.max(np.abs(c.host(rd) - ref)) < 1e-12 * np.abs(ref).max()
     assert abs(n2.item() - np.linalg.norm(ref) ** 2) < 1e-11 * np.linalg.norm(ref) ** 2
+
+
+@pytest.mark.parametrize("model", ["heisenberg_f64", "asep_c128"])
+def test_gauge_shortcut_and_solver_options(P, model):
+    """run_dmrg(twoSite=True) with gauge_shortcut / max_space / precond against the plain run on the device: same
+    energy (1e-10) and entropy (1e-8); the shortcut is taken, the larger subspace and the preconditioner do not cost
+    mat-vecs."""
+    if model == "heisenberg_f64":
+        mpo, dtype, chi = P.mpo.heisenberg_mpo(18), "f64", 64
+    else:
+        mpo, dtype, chi = P.mpo.asep_mpo(18, PRM), "c128", 64
+    res = {}
+    for tag, opts in (("plain", {}), ("shortcut", {"gauge_shortcut": True}), ("space", {"max_space": 24}), ("precond", {"precond": "diag"})):
+        np.random.seed(2)
+        st = {}
+        out = P.dmrg.run_dmrg(mpo, mbd=chi, tol=0.0, maxIter=6, twoSite=True, dtype=dtype, stats=st, res_tol=1e-10, **opts)
+        res[tag] = (out[0], out[1], st)
+    E0, EE0 = res["plain"][0], res["plain"][1]
+    for tag in ("shortcut", "space", "precond"):
+        assert abs(res[tag][0] - E0) < 1e-10 * abs(E0), tag
+        assert abs(res[tag][1] - EE0) < 1e-8, tag
+    assert res["shortcut"][2].get("n_gauge_moves", 0) > 0
+    assert res["space"][2]["n_matvec"] <= 1.05 * res["plain"][2]["n_matvec"]
+    assert res["precond"][2]["n_matvec"] <= 1.05 * res["plain"][2]["n_matvec"]
