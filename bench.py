@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip bond-step / cpu-baseline extras")
     ap.add_argument("--no-full-sweep", action="store_true", help="skip the measured two-site sweeps of the N=100 chain (~1 min)")
     ap.add_argument("--svd", default="auto", choices=["auto", "gesvd", "gesvdj", "gram"])
+    ap.add_argument("--gauge-shortcut", action="store_true",
+                    help="N = 1: also time the converged sweeps with run_dmrg's gauge_shortcut option (sweep_sec_shortcut); off by "
+                         "default until validated on a GPU")
     ap.add_argument("--sharded-sweep", action="store_true",
                     help="N > 1: also time two-site sweeps of the N=100 chain with the mat-vecs and block updates of the large "
                          "bonds sharded over the ranks (run_dmrg(shard=...)); off by default until validated on GPUs")
@@ -386,6 +389,8 @@ def main():
         line["scan"] = scan_sample()
         if not args.no_full_sweep:
             line["sweep_sec"] = full_sweep(args, ctx)
+            if args.gauge_shortcut:
+                line["sweep_sec_shortcut"] = full_sweep(args, ctx, gauge_shortcut=True)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -567,7 +572,7 @@ def scan_sample():
             "E": [float(np.real(e)) for e in res["E"]], "E_imag_max": float(np.max(np.abs(np.imag(res["E"]))))}
 
 
-def full_sweep(args, ctx, shard=None):
+def full_sweep(args, ctx, shard=None, gauge_shortcut=False):
     """Measured two-site sweeps (right + left over all 99 bonds) of the TASEP N=100 chain at chi: the state is
     grown through a [16, 64, 256] chi ramp (so it is physical) and then swept five times with mbd = chi.  Two-site
     sweeps are not zero-padded: every bond grows by up to a factor d per visit, so the first two sweeps run on
@@ -584,6 +589,8 @@ def full_sweep(args, ctx, shard=None):
     sched = [c for c in (16, 64, 256) if c < chi]
     t0 = time.perf_counter()
     extra = {} if shard is None else {"shard": shard}
+    if gauge_shortcut:
+        extra["gauge_shortcut"] = True
     dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=True, ctx=ctx, **extra)
     mpsL, _ = mps_tools.load_mps(os.path.join(tmp, "st_mbd%d" % (len(sched) - 1)))
     mpsL = [[ctx.dev(t) for t in mpsL[0]]]
@@ -601,6 +608,7 @@ def full_sweep(args, ctx, shard=None):
             "E": [float(np.real(E)), float(np.imag(E))], "EE": float(EE), "n_matvec": stats.get("n_matvec"),
             "bonds": 2 * (N - 1), "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0),
             "n_sharded_solves": stats.get("n_sharded_solves", 0), "n_sharded_env": stats.get("n_sharded_env", 0),
+            "n_gauge_moves": stats.get("n_gauge_moves", 0),
             "how": "measured: TASEP N=%d chi=%d c128 two-site sweeps after a %s ramp" % (N, chi, sched)}
 
 
