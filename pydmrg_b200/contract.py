@@ -19,8 +19,12 @@ def full_contract(mpo=None, mps=None, lmps=None, state=None, lstate=None, orth=F
     if isinstance(lmps, str):
         lmps, glSite = mps_tools.load_mps(lmps)
     assert not (lmps is None and mps is None)
-    if orth:
-        raise NotImplementedError("orth=True (orthonormalize_states) is host-side post-processing of the reference")
+    if orth:                                                     # contract.py:16-19
+        host = lambda L: [[np.array(ctx.host(t)) for t in M] for M in L]
+        if mps is not None:
+            mps = mps_tools.orthonormalize_states(host(mps), gSite=gSite)
+        if lmps is not None:
+            lmps = mps_tools.orthonormalize_states(host(lmps), gSite=glSite)
     if state is None and lstate is None:
         state, lstate = 0, 0
     elif state is None:

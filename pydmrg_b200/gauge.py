@@ -95,10 +95,14 @@ def make_mps_right(M, ctx=None):
     return M
 
 
-def calc_entanglement_all(mpsList, gSite=0, ctx=None):
-    """Entanglement entropy of every bond and every state, tools/aux/process_states.py:5-27 without the optional
-    orthonormalisation of the states: the centre is moved to the right end and swept back, the entropy of bond
-    (site-1, site) is read off each SVD.  Returns EE (nStates, N-1); the states are left right-canonical."""
+def calc_entanglement_all(mpsList, gSite=0, ctx=None, orth=False):
+    """Entanglement entropy of every bond and every state, tools/aux/process_states.py:5-27: the centre is moved to the
+    right end and swept back, the entropy of bond (site-1, site) is read off each SVD.  ``orth``: orthonormalise the
+    states' centre tensors first (mps_tools.orthonormalize_states, :14-15; host arrays).  Returns EE (nStates, N-1);
+    the states are left right-canonical."""
+    if orth:
+        from . import mps as mps_tools
+        mpsList = mps_tools.orthonormalize_states(mpsList, gSite=gSite)
     nStates, N = len(mpsList), len(mpsList[0])
     EE = np.zeros((nStates, N - 1))
     for state in range(nStates):

@@ -59,6 +59,26 @@ def conj_mps(mps):
     return [[np.conj(t) for t in M] for M in mps]
 
 
+def orthonormalize_states(mps, mpo=None, gSite=None, printEnergies=False):
+    """tools/mps_tools.py:392-430: the centre tensors of all states (every other site tensor is shared, they are
+    the state-averaged isometries) are replaced by an orthonormal basis of their span -- ``scipy.linalg.orth`` of the
+    (d*Dl*Dr, nStates) matrix, exactly the reference's call.  Host-side post-processing of saved / returned states
+    (the energy print-outs of the reference are omitted; ``mpo`` is accepted for signature compatibility)."""
+    import scipy.linalg as sla
+    if isinstance(mps, str):
+        mps, gSite = load_mps(mps)
+    gSite = int(gSite)
+    nStates = len(mps)
+    shape = np.shape(mps[0][gSite])
+    vecs = np.zeros((int(np.prod(shape)), nStates), dtype=np.complex128)
+    for state in range(nStates):
+        vecs[:, state] = np.reshape(mps[state][gSite], -1)
+    vecs = sla.orth(vecs, rcond=1e-100)                                  # :416
+    for state in range(nStates):
+        mps[state][gSite] = np.reshape(vecs[:, state], shape)
+    return mps
+
+
 def increase_mbd(M, mbd, d=2):
     """Zero-pad every site tensor to the bond profile of a larger chi (open chain).
     tools/mps_tools.py:244-279 (periodic=False, constant=False branch)."""

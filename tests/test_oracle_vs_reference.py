@@ -108,3 +108,22 @@ def test_saved_states_round_trip_between_reference_and_product(ref, tmp_path):
         mps_tools.save_mps(mpsL, b, gaugeSite=3, fformat=fmt)
         got, gs = ref.mps_tools.load_mps(b, fformat=fmt)
         assert int(gs) == 3 and all(np.array_equal(x, y) for s in range(2) for x, y in zip(got[s], mpsL[s]))
+
+
+def test_orthonormalize_states_equals_reference(ref):
+    """tools/mps_tools.py:392-430 (used by full_contract(orth=True) and the scan scripts' post-processing)."""
+    from pydmrg_b200 import mps as mps_tools
+    rng = np.random.default_rng(2)
+    shapes = ((2, 1, 2), (2, 2, 4), (2, 4, 2), (2, 2, 1))
+    shared = [crand(rng, *s) for s in shapes]
+    mpsL = [[t.copy() for t in shared] for _ in range(2)]
+    for st in range(2):
+        mpsL[st][2] = crand(rng, *shapes[2])                       # only the centre tensors differ between the states
+    with quiet():
+        a = ref.mps_tools.orthonormalize_states([[t.copy() for t in M] for M in mpsL], gSite=2)
+    b = mps_tools.orthonormalize_states([[t.copy() for t in M] for M in mpsL], gSite=2)
+    for st in range(2):
+        for x, y in zip(a[st], b[st]):
+            assert np.array_equal(x, y)
+    c0, c1 = b[0][2].ravel(), b[1][2].ravel()
+    assert abs(np.vdot(c0, c1)) < 1e-13 and abs(np.vdot(c0, c0) - 1) < 1e-13

@@ -416,3 +416,28 @@ def test_gauge_shortcut_for_unchanged_bonds(E):
     # one-site sweeps ignore the option
     np.random.seed(2)
     dmrg.run_dmrg(mpo, mbd=8, tol=1e-6, maxIter=1, ctx=ctx, native=False, gauge_shortcut=True)
+
+
+def test_full_contract_with_orthonormalised_states(E, golden):
+    """full_contract(orth=True) (tools/contract.py:16-19 -> orthonormalize_states, mps_tools.py:392-430) on the two
+    states returned by a nStates = 2 run: orthonormal after the call.  (scipy.linalg.orth returns a basis of the SPAN,
+    so the individual states are mixed -- the reference's own comment at mps_tools.py:416 says "something is wrong
+    here"; the product reproduces the reference's arrays bit for bit, tests/test_oracle_vs_reference.py.)"""
+    from pydmrg_b200 import contract, dmrg, mpo as M
+    g = golden["multistate"]
+    mpo = M.asep_mpo(6, tuple(float(v) for v in g["params"]))
+    ctx = E.Context("c128")
+    np.random.seed(6)
+    gs = 4
+    E0, EE, gap, mps = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=5, nStates=2, ctx=ctx, native=False, res_tol=1e-10,
+                                     returnState=True, gaugeSiteSave=gs)
+    bra = [[np.conj(t) for t in Mst] for Mst in mps]
+    kw = dict(mps=mps, lmps=bra, orth=True, gSite=gs, glSite=gs, ctx=ctx)
+    n00 = contract.full_contract(state=0, lstate=0, **kw)
+    n01 = contract.full_contract(state=1, lstate=0, **kw)
+    assert abs(n00 - 1) < 1e-12 and abs(n01) < 1e-12
+    e0 = contract.full_contract(mpo=mpo, state=0, lstate=0, **kw) / n00
+    e1 = contract.full_contract(mpo=mpo, state=1, lstate=1, **kw)
+    ed = g["asep6_ed"]
+    lo, hi = min(ed[0].real, ed[1].real), max(ed[0].real, ed[1].real)
+    assert lo - 1e-6 < e0.real < hi + 1e-6 and lo - 1e-6 < e1.real < hi + 1e-6    # both live in the two-state span
