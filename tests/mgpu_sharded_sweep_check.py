@@ -20,8 +20,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl")
+    emulate = os.environ.get("PDMRG_CHECK_EMULATE") == "1"      # CPU dry run of THIS script: gloo + tests/emu_device.py
+    dev = "cpu" if emulate else "cuda"
+    if emulate:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        os.environ["PDMRG_PY_DAVIDSON"] = "1"
+        import emu_device
+        emu_device.install(setattr)
+        from pydmrg_b200 import core
+        core.default_context = lambda dtype="c128": emu_device.Context(dtype)
+        import pydmrg_b200.dmrg as _d
+        _d.default_context = core.default_context
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl")
     from pydmrg_b200 import dmrg, mpo as M, parallel
     chi = int(os.environ.get("PDMRG_CHECK_CHI", "64"))
     N = int(os.environ.get("PDMRG_CHECK_N", "16"))
@@ -42,7 +55,7 @@ def main():
         for mode in ("ket", "bond"):
             E, EE, ns, nmv, nenv = res[mode]
             # every rank must hold the same numbers as rank 0
-            t = torch.tensor([E.real, E.imag, EE], dtype=torch.float64, device="cuda")
+            t = torch.tensor([E.real, E.imag, EE], dtype=torch.float64, device=dev)
             t0 = t.clone(); dist.broadcast(t0, 0)
             same = bool(torch.equal(t, t0))
             good = abs(E - E0) < 1e-10 * abs(E0) and abs(EE - EE0) < 1e-8 and ns > 0 and nenv > 0 and same
@@ -73,7 +86,7 @@ def main():
                                                              "sharded_block_updates": st.get("n_sharded_env", 0)}
             del mpsL, F, cache
             torch.cuda.empty_cache()
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         report["ok"] = bool(flag.item())

@@ -289,3 +289,23 @@ def test_diagonal_preconditioner_same_eigenpair_fewer_matvecs(monkeypatch, golde
     assert abs(out[True][0] - g["exact_min_real"]) < 1e-9 * abs(g["exact_min_real"])
     assert abs(abs(np.vdot(out[True][2], out[False][2])) - 1) < 1e-8
     assert out[True][1] < out[False][1]
+
+
+def test_sharded_sweep_check_script_dry_run_on_two_gloo_ranks():
+    """tests/mgpu_sharded_sweep_check.py (the multi-GPU check of sharded sweeps) executed as it is on two gloo ranks
+    over the emulated device entry points (PDMRG_CHECK_EMULATE=1): ASEP c128 and Heisenberg f64, ket and bond mode,
+    real ShardedHeff / ShardSpec / env_update code paths -- the script must report ok."""
+    import json
+    import subprocess
+    port = 36500 + (os.getpid() % 1500)
+    env = dict(os.environ, PDMRG_CHECK_EMULATE="1", PDMRG_CHECK_CHI="32", PDMRG_CHECK_N="12", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(HERE, "mgpu_sharded_sweep_check.py")],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    rep = json.loads(line)
+    assert rep["ok"] and rep["world"] == 2
+    for key in ("asep_ket", "asep_bond", "heisenberg_ket", "heisenberg_bond"):
+        assert rep[key]["sharded_solves"] > 0 and rep[key]["sharded_block_updates"] > 0 and rep[key]["same_on_all_ranks"]
+        assert rep[key]["dE"] < 1e-9
