@@ -38,7 +38,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TASEP = (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, -0.5)
+# TASEP s-ensemble point of the benchmark: s = +0.5 is the current-ENHANCED side (hops carry e^{+s}), an entangled state
+# (EE = 0.83 at N=100); round 1 used s = -0.5, whose dominant state is a product state (EE = 1e-15: nothing to solve)
+TASEP = (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, 0.5)
 FP64_PEAK_FALLBACK_TFLOPS = 36.9      # profiles/fp64_peaks_r01.json (cuBLAS zgemm 8192^3 burst, this pool)
 
 
@@ -114,41 +116,116 @@ def heff2_flops(chi, d=2, w=6, cplx=True):
 
 
 # ---------------------------------------------------------------------------------------------
+def seeded_operands(chi, seed=0):
+    """The bench operands as HOST arrays, seeded: identical in both arms and in the parity check."""
+    rng = np.random.default_rng(seed)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    return cr(chi, 6, chi), cr(chi, 6, chi), cr(2, 2, chi, chi)
+
+
 def run_reference(args, rank, world):
-    """Oracle port of the reference's CPU path; bounded sample (chi_sample) of the same closure."""
+    """The reference's CPU implementation of the step (oracle port: the un-optimised np.einsum calls of
+    diag_tools.py:153-156, single-threaded c_einsum) on the SAME configuration as the GPU arm, chi=1024.  A full call
+    takes ~60 s, so a step is a bounded sample of it: every stage of the reference's contraction carries the bra index
+    r of the right block, so restricting R to a slab of chi/16 rows computes exactly y[..., slab] with exactly 1/16 of
+    the FLOPs of every stage -- step k takes slab k mod 16.  ONE full call is timed as well (size / slab insensitivity)."""
     if rank != 0:
         return
     from oracle import dmrg_oracle as orc
     from pydmrg_b200 import mpo as M
-    chi = args.ref_chi
     W1, W2 = M.asep_mpo(6, TASEP)[0][2:4]
-    rng = np.random.default_rng(0)
-    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
-    L, R, x = cr(chi, 6, chi), cr(chi, 6, chi), cr(2, 2, chi, chi)
-    f = lambda: orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "einsum")
-    for _ in range(min(args.warmup, 1)):
-        f()
+    chi, nslab = args.chi, 16
+    L, R, x = seeded_operands(chi)
+    rows = chi // nslab
+    slab = lambda k: _slab_call(orc, x, L, W1, W2, R, k % nslab, rows)
+    for k in range(args.warmup):
+        slab(k)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        f()
-    dt = (time.perf_counter() - t0) / args.steps
+    for k in range(args.steps):
+        slab(k)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
     fl = heff2_flops(chi)
-    val = fl / dt * 1e-9
+    val = (fl / nslab) / dt * 1e-9
+    full = None
+    if not args.no_extras:
+        t0 = time.perf_counter()
+        yfull = orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "einsum")
+        full = time.perf_counter() - t0
+        ys = _slab_call(orc, x, L, W1, W2, R, 3, rows)
+        slab_err = float(np.linalg.norm(ys - yfull.reshape(x.shape)[..., 3 * rows:4 * rows].reshape(-1)) / np.linalg.norm(ys))
     # BLAS-fair variant (same contractions through threaded zgemm), reported alongside
     tb = time.perf_counter(); orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "blas"); tb = time.perf_counter() - tb
     line = {"impl": "reference", "metric": "heff_matvec_fp64_gflops", "value": val, "unit": "GFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": "TASEP N=100 chi=1024 two-site H_eff mat-vec (d=2,w=6,c128)", "chi": 1024,
-                       "sample_chi": chi},
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "c128",
+            "data": "synthetic",
+            "config": workload_config(chi),
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-                             "sample": "two-site Hfun, un-optimised np.einsum exactly as diag_tools.py:153-156, chi=%d "
-                                       "(c_einsum is single-threaded and not BLAS; GFLOP/s is size-insensitive), %d steps"
-                                       % (chi, args.steps),
+                             "sample": "per step: the chi=%d two-site Hfun of the GPU arm restricted to a slab of %d of the %d right-bond "
+                                       "rows (1/%d of the FLOPs of every einsum stage of diag_tools.py:153-156; un-optimised np.einsum = "
+                                       "single-threaded c_einsum); %d steps" % (chi, rows, chi, nslab, args.steps),
+                             "full_call_sec": full, "full_call_gflops": (fl / full * 1e-9) if full else None,
+                             "slab_vs_full_rel_err": slab_err if full else None,
                              "blas_fair_gflops": fl / tb * 1e-9, "blas_fair_cores": os.cpu_count()},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _slab_call(orc, x, L, W1, W2, R, k, rows):
+    """y[..., k*rows:(k+1)*rows] of the two-site Hfun through the reference's four einsum stages (r restricted)."""
+    Rk = R[k * rows:(k + 1) * rows]
+    xr = x
+    s1 = np.einsum("ros,nqks->ronqk", Rk, xr)                    # diag_tools.py:153
+    s2 = np.einsum("lopq,ronqk->lprnk", W2, s1)                  # :154
+    s3 = np.einsum("jlmn,lprnk->jmprk", W1, s2)                  # :155
+    return -np.einsum("ijk,jmprk->mpir", L, s3).reshape(-1)      # :156, :162
+
+
+def workload_config(chi):
+    return {"workload": "TASEP (alpha=0.35, beta=2/3, s=+0.5) N=100 chi=%d two-site H_eff mat-vec (d=2,w=6,c128); BASELINE configs[2]" % chi,
+            "chi": chi, "N": 100, "d": 2, "w": 6, "flops_per_step": heff2_flops(chi),
+            "l2": "operands 96+96+64 MiB and the 384 MiB intermediate exceed the 126 MB L2; no flush needed"}
+
+
+def measure_fp64_peak(reps=3, n=8192):
+    """FP64 tensor-pipe denominator measured NOW on this box: cuBLAS Zgemm n^3 through torch.matmul (a library call used
+    only as the yardstick; MEASURED_PEAKS.json has no FP64 entry).  Best of ``reps``."""
+    import torch
+    try:
+        a = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+        b = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+        torch.matmul(a, b)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            torch.matmul(a, b)
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 8.0 * n ** 3 / (best * 1e-3) * 1e-12
+    except Exception:
+        return None
+
+
+def timed_loop(fn, steps, barrier, dist, world):
+    """K calls bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks -> ms per step."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 # ---------------------------------------------------------------------------------------------
@@ -162,14 +239,14 @@ def main():
     ap.add_argument("--ref-chi", type=int, default=256)
     ap.add_argument("--davidson-cycles", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true", help="skip bond-step / cpu-baseline extras")
-    ap.add_argument("--no-full-sweep", action="store_true", help="skip the measured two-site sweeps of the N=100 chain (~1 min)")
+    ap.add_argument("--no-full-sweep", action="store_true", help="skip the measured two-site sweeps of the N=100 chain (~2 min)")
     ap.add_argument("--svd", default="auto", choices=["auto", "gesvd", "gesvdj", "gram"])
-    ap.add_argument("--gauge-shortcut", action="store_true",
-                    help="N = 1: also time the converged sweeps with run_dmrg's gauge_shortcut option (sweep_sec_shortcut); off by "
-                         "default until validated on a GPU")
+    ap.add_argument("--gauge-shortcut", action="store_true", help="N = 1: also time the sweeps with run_dmrg's gauge_shortcut option")
     ap.add_argument("--sharded-sweep", action="store_true",
                     help="N > 1: also time two-site sweeps of the N=100 chain with the mat-vecs and block updates of the large "
-                         "bonds sharded over the ranks (run_dmrg(shard=...)); off by default until validated on GPUs")
+                         "bonds sharded over the ranks (run_dmrg(shard=...))")
+    ap.add_argument("--scan-points", type=int, default=0, help="N > 1: also run this many points of the configs[3] scan "
+                                                                  "(dynamic scheduling over the ranks) and report points/hour")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -185,17 +262,15 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from pydmrg_b200 import core, device as D, mpo as M, parallel
+    from pydmrg_b200 import core, device as D, eigs, mpo as M, parallel
     from pydmrg_b200._lib import launch_count
 
     chi, d, w = args.chi, 2, 6
     ctx = core.Context("c128", svd_method=args.svd)
-    # scan point of this rank (weak scaling: same shape, different s)
-    s_val = TASEP[6] + 0.05 * rank
-    prm = TASEP[:6] + (s_val,)
-    W1, W2 = M.asep_mpo(6, prm)[0][2:4]
+    W1, W2 = M.asep_mpo(6, TASEP)[0][2:4]
     Wc = D.combine_twosite(W1, W2, np.complex128)
-    g = torch.Generator(device="cuda"); g.manual_seed(1234 + rank)
+    # identical seeded operands on every rank (the N > 1 headline is ONE mat-vec strong-scaled over the ranks)
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
     rnd = lambda *s: torch.randn(*s, dtype=torch.complex128, device="cuda", generator=g)
     L, R = rnd(chi, w, chi), rnd(chi, w, chi)
     x = rnd(d * d * chi * chi)
@@ -209,51 +284,77 @@ def main():
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
+    # ---- the step: N = 1 the plain mat-vec; N > 1 the SAME mat-vec split over the ranks (strong scaling) ------------
+    sharded_variants = {}
+    parity = {}
+    if world == 1:
+        step, how = (lambda: plan.apply(x, y)), "single GPU"
+    else:
         plan.apply(x, y)
+        y_ref = y.clone()
+
+        def check(tag, obj, yy):
+            obj.apply(x, yy)
+            torch.cuda.synchronize()
+            err = float((torch.linalg.vector_norm(yy - y_ref) / torch.linalg.vector_norm(y_ref)).item())
+            y0 = yy.clone()
+            dist.broadcast(torch.view_as_real(y0), src=0)
+            same = torch.tensor([1 if torch.equal(y0, yy) else 0], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            parity[tag] = {"rel_err_vs_unsharded": err, "bit_identical_on_all_ranks": bool(same.item())}
+
+        ops1 = [(L, Wc, R)]
+        ys = torch.empty_like(x)
+        objs = {"bond_nccl": parallel.ShardedHeff(D.C128, d * d, chi, chi, ops1, ctx.ws, rank, world, dist),
+                "bond_fused": parallel.FusedShardedHeff(D.C128, d * d, chi, chi, ops1, ctx.ws, rank, world, dist),
+                "ket_nccl": parallel.ShardedHeff(D.C128, d * d, chi, chi, ops1, ctx.ws, rank, world, dist, mode="ket"),
+                "ket_fused": parallel.FusedShardedHeff(D.C128, d * d, chi, chi, ops1, ctx.ws, rank, world, dist, mode="ket")}
+        for tag, obj in objs.items():
+            check(tag, obj, ys)
+        head = objs["ket_fused"]
+        step, how = (lambda: head.apply(x, ys)), ("ONE mat-vec split %d ways over the left ket index; stage C = one long-K GEMM "
+                                                  "whose scatter epilogue reduce-scatters the partial y over NVLink, then a "
+                                                  "flag-guarded reduce + all-gather kernel (no NCCL on the data path)" % world)
+
+    for _ in range(args.warmup):
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        plan.apply(x, y)
-    e1.record()
-    barrier()
+    ms_step = timed_loop(step, args.steps, barrier, dist, world)
     launches = launch_count() - n0
-    ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * flops / (ms_step * 1e-3) * 1e-9
+    value = flops / (ms_step * 1e-3) * 1e-9
 
-    # ---- per-stage timing of the same step (roofline of the dominant kernel) -----------------
+    # ---- per-stage timing of the single-GPU step (roofline of the dominant kernel) --------------------------------
     st = np.zeros(3)
     nrep = max(3, min(args.steps, 10))
     for _ in range(nrep):
         st += np.array(plan.apply_timed(x, y))
     st /= nrep
+    ms_single = timed_loop(lambda: plan.apply(x, y), max(3, min(args.steps, 10)), barrier, dist, world) if world > 1 else ms_step
     # FLOPs the two GEMM launches actually execute: chi^3 terms of the non-empty MPO slabs (for TASEP
     # rows 3,4 of W are zero, so stage C runs 4 of 6 slabs); complex MAC = 8 FLOP
     cube = plan.flops_gemm
     gemm_ms = st[0] + st[2]
-    peak, peak_src = fp64_peak()
+    peak_now = measure_fp64_peak() if rank == 0 or world == 1 else None
+    peak_file, peak_src = fp64_peak()
+    peak = peak_now if peak_now else peak_file
     achieved = cube / (gemm_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": "gemm_nt_dmma_kernel<c128> (FP64 DMMA.8x8x4, TMA-fed)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src + " (FP64 tensor pipe; measured on this pool)",
+                "traffic": None,
+                "peak_source": ("cuBLAS Zgemm 8192^3 measured in this run (fp64_peak_measured_now)" if peak_now else peak_src)
+                               + "; FP64 tensor pipe, MEASURED_PEAKS.json has no FP64 entry",
+                "fp64_peak_measured_now": peak_now, "fp64_peak_committed": peak_file,
                 "launches_per_step": 2, "flops_per_launch_avg": cube / 2, "ms_per_launch_avg": gemm_ms / 2,
                 "note": "achieved counts EXECUTED GEMM FLOPs (MPO block sparsity skipped); the headline value "
-                        "counts the dense-W algorithmic FLOPs of SURVEY 8d",
+                        "counts the dense-W algorithmic FLOPs of SURVEY 8d; measured on the single-GPU step",
                 "dense_algorithmic_flops_per_step": flops, "executed_gemm_flops_per_step": cube,
                 "stage_ms": {"gemm_stage_A": st[0], "mix": st[1], "gemm_stage_C": st[2]},
-                "share_of_step": gemm_ms / ms_step}
+                "share_of_step": gemm_ms / ms_single}
     tr = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tr):
         try:
@@ -261,18 +362,33 @@ def main():
         except Exception:
             pass
 
-    # ---- e2e: the reference-shaped closure with HOST buffers ---------------------------------
-    xh = torch.empty(x.shape, dtype=x.dtype).pin_memory()
-    yh = torch.empty(x.shape, dtype=x.dtype).pin_memory()
+    # ---- e2e: the product's reference-shaped closure, HOST vector in, HOST vector out ------------------------------
+    nbytes = x.numel() * 16
+    xh = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
     xh.copy_(x)
+    xh_np = xh.numpy()
     e2e_steps = max(3, min(args.steps, 10))
+    if world == 1:
+        # eigs.make_ham_func(M, W, F, site, oneSite=False) -- the two-slot [L, R] addressing of the reference's closure
+        dummyA, dummyB = torch.empty((d, chi, 1), dtype=x.dtype, device="cuda"), torch.empty((d, 1, chi), dtype=x.dtype, device="cuda")
+        Hfun = eigs.make_ham_func([dummyA, dummyB], [[W1, W2]], [[L, R]], 0, oneSite=False, ctx=ctx)[0]
+        holder = {}
 
-    def e2e_step():
-        x.copy_(xh, non_blocking=True)
-        plan.apply(x, y)
-        yh.copy_(y, non_blocking=True)
-        torch.cuda.synchronize()
+        def e2e_step():
+            holder["y"] = Hfun(xh_np)                            # H2D of x, mat-vec, D2H of y, synchronised
 
+        api = "pydmrg_b200.eigs.make_ham_func(M, W, F, site, oneSite=False)[0](x_host: ndarray) -> y_host: ndarray"
+    else:
+        yh = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        xd2 = torch.empty_like(x)
+
+        def e2e_step():
+            xd2.copy_(xh, non_blocking=True)                     # every rank needs x; every rank ends with y
+            head.apply(xd2, ys)
+            yh.copy_(ys, non_blocking=True)
+            torch.cuda.synchronize()
+
+        api = "FusedShardedHeff(mode='ket').apply with pinned host x / y on every rank"
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -284,89 +400,35 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    nbytes = x.numel() * 16
-    e2e = {"value": world * flops / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes * world,
-           "d2h_bytes_per_step": nbytes * world, "ms_per_step": e2e_ms,
-           "api": "Hfun(x_host) -> y_host  (make_ham_func closure; pinned buffers; L,R,W bound at closure creation)"}
+    e2e = {"value": flops / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world, "ms_per_step": e2e_ms, "api": api}
 
+    cfg = workload_config(chi)
+    cfg["parallelism"] = how
     line = {"metric": "heff_matvec_fp64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": "TASEP N=100 chi=%d two-site H_eff mat-vec (d=2,w=6,c128); BASELINE configs[2]" % chi,
-                       "chi": chi, "N": 100, "d": d, "w": w, "flops_per_step": flops,
-                       "l2": "operands 96+96+64 MiB and the 384 MiB intermediate exceed the 126 MB L2; no flush needed",
-                       "parallelism": "1 scan point per GPU" if world > 1 else "single GPU"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 
-    # ---- MPO-bond-sharded mat-vec with one NCCL all-reduce (strong scaling), N > 1 --------------
     if world > 1:
-        torch.manual_seed(99)    # identical operands on every rank
-        gs = torch.Generator(device="cuda"); gs.manual_seed(99)
-        rs = lambda *s: torch.randn(*s, dtype=torch.complex128, device="cuda", generator=gs)
-        Ls, Rs, xs = rs(chi, w, chi), rs(chi, w, chi), rs(d * d * chi * chi)
-        W1s, W2s = M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5))[0][2:4]
-        Wcs = D.combine_twosite(W1s, W2s, np.complex128)
-        sh = parallel.ShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist)
-        ys = torch.empty_like(xs)
-        for _ in range(3):
-            sh.apply(xs, ys)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            sh.apply(xs, ys)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        per, ideal = parallel.partition_cost(sh.partition[0])
-        line["sharded"] = {"what": "one chi=%d two-site mat-vec (dense ASEP W) split over the MPO bond" % chi,
-                           "nccl_allreduce": {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9},
-                           "scaling": "strong", "slab_gemms_per_rank": per, "ideal_speedup": ideal}
-        # same decomposition, exchange fused into the kernels over peer memory (no NCCL on the data path)
-        fz = parallel.FusedShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist)
-        for _ in range(3):
-            fz.apply(xs, ys)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            fz.apply(xs, ys)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        line["sharded"]["fused_peer_memory"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
-                                                "how": "GEMM scatter epilogue (peer st.global) + flag-guarded reduce/all-gather kernel"}
-        fz.close()
-        # ket-index sharding: every rank does 1/N of both GEMM stages, one NCCL all-reduce
-        kz = parallel.ShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist, mode="ket")
-        for _ in range(3):
-            kz.apply(xs, ys)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            kz.apply(xs, ys)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        line["sharded"]["ket_split_nccl"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
-                                             "how": "left ket index split N ways (balanced), 1 NCCL all-reduce of y"}
-        # the same split with the exchange fused into the kernels (long-K stage C, scatter epilogue, peer stores)
-        fk = parallel.FusedShardedHeff(D.C128, d * d, chi, chi, [(Ls, Wcs, Rs)], ctx.ws, rank, world, dist, mode="ket")
-        for _ in range(3):
-            fk.apply(xs, ys)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            fk.apply(xs, ys)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        line["sharded"]["ket_split_fused"] = {"ms_per_matvec": float(t.item()), "gflops": flops / (t.item() * 1e-3) * 1e-9,
-                                              "how": "ket split; stage C = one long-K GEMM whose scatter epilogue reduce-scatters the "
-                                                     "partial y over NVLink, then a flag-guarded reduce + all-gather kernel (no NCCL)"}
-        fk.close()
+        line["ms_per_step_unsharded_one_gpu"] = ms_single
+        line["speedup_vs_one_gpu"] = ms_single / ms_step
+        for tag, obj in objs.items():
+            for _ in range(3):
+                obj.apply(x, ys)
+            ms = timed_loop(lambda: obj.apply(x, ys), args.steps, barrier, dist, world)
+            sharded_variants[tag] = {"ms_per_matvec": ms, "gflops": flops / (ms * 1e-3) * 1e-9, "speedup": ms_single / ms, **parity[tag]}
+        per, ideal = parallel.partition_cost(objs["bond_nccl"].partition[0])
+        line["sharded"] = {"what": "one chi=%d two-site mat-vec split over the ranks; every variant checked against the unsharded "
+                                   "result on the same operands (rel_err) and for bit-identical y on all ranks" % chi,
+                           "variants": sharded_variants, "bond_split_slab_gemms_per_rank": per, "bond_split_ideal_speedup": ideal}
+        # weak scaling for the record (N independent mat-vecs, no collective: cannot fail)
+        ms_w = timed_loop(lambda: plan.apply(x, y), args.steps, barrier, dist, world)
+        line["weak_replicas"] = {"ms_per_step": ms_w, "aggregate_gflops": world * flops / (ms_w * 1e-3) * 1e-9}
+        for obj in (objs["bond_fused"], objs["ket_fused"]):
+            obj.close()
+        if args.scan_points:
+            line["scan"] = scan_multi(args.scan_points, rank, world, dist)
 
     if world > 1 and args.sharded_sweep:
         spec = parallel.ShardSpec(rank, world, dist, mode="ket")
@@ -376,16 +438,17 @@ def main():
 
     # ---- extras on rank 0 at N=1: bond step, sweep estimate, CPU baseline ----------------------
     if world == 1 and not args.no_extras:
+        line["cpu_baseline"] = cpu_baseline(args, ctx)
+        line["parity_rel_err"] = line["cpu_baseline"]["parity_rel_err"]
         line["bond_step"] = bond_step(args, ctx, plan, L, R, W1, W2, chi)
         bs = line["bond_step"]
         nb = 2 * 99
         line["sweep_sec_derived"] = {"value": bs["ms_total_recycled"] * nb * 1e-3,
                                      "how": "198 bond steps x measured chi=%d bond step with %d Davidson cycles each and the "
-                                            "warm-started truncation; upper bound (edge bonds are smaller, a converged sweep "
-                                            "needs 1 cycle per bond)" % (chi, args.davidson_cycles)}
+                                            "warm-started truncation (edge bonds are smaller)" % (chi, args.davidson_cycles)}
         line["krylov"] = krylov_bandwidth(chi)
+        line["small_chi_matvec"] = small_chi_matvec()
         line["config4_matvec"] = config4_matvec()
-        line["cpu_baseline"] = cpu_baseline(args)
         line["scan"] = scan_sample()
         if not args.no_full_sweep:
             line["sweep_sec"] = full_sweep(args, ctx)
@@ -526,50 +589,118 @@ def config4_matvec(chi=2048, reps=10):
     return out
 
 
-def cpu_baseline(args):
-    """Oracle port on this box's host cores: (A) the reference's own un-optimised einsum calls
-    (single-threaded), (B) the BLAS-fair restatement on all cores.  Bounded: ~10-20 s."""
+def cpu_baseline(args, ctx):
+    """Oracle port on this box's host cores, on a bounded sample of the SAME chi=1024 workload: (A) the reference's own
+    un-optimised einsum calls (single-threaded c_einsum) on r-slabs of the mat-vec (see run_reference), (B) the BLAS-fair
+    restatement on all cores, one full call -- whose output is also the parity check of the GPU result on the same
+    seeded operands (``parity_rel_err``, the oracle as the checker)."""
+    import torch
     from oracle import dmrg_oracle as orc
-    from pydmrg_b200 import mpo as M
+    from pydmrg_b200 import device as D, mpo as M
     W1, W2 = M.asep_mpo(6, TASEP)[0][2:4]
-    rng = np.random.default_rng(0)
-    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
-    chi_a = args.ref_chi
-    L, R, x = cr(chi_a, 6, chi_a), cr(chi_a, 6, chi_a), cr(2, 2, chi_a, chi_a)
+    chi, nslab = args.chi, 16
+    rows = chi // nslab
+    L, R, x = seeded_operands(chi)
     t = time.perf_counter(); n = 0
-    while n < 3 or (time.perf_counter() - t < 5 and n < 10):
-        orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "einsum"); n += 1
+    while n < 2 or (time.perf_counter() - t < 12 and n < nslab):
+        _slab_call(orc, x, L, W1, W2, R, n % nslab, rows); n += 1
     ta = (time.perf_counter() - t) / n
-    chi_b = min(args.chi, 1024)
-    L, R, x = cr(chi_b, 6, chi_b), cr(chi_b, 6, chi_b), cr(2, 2, chi_b, chi_b)
-    orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "blas")
     t = time.perf_counter()
-    orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "blas")
+    ref = orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "blas")
     tb = time.perf_counter() - t
-    return {"value": heff2_flops(chi_a) / ta * 1e-9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-            "sample": "reference-faithful two-site Hfun (np.einsum, no optimize: single-threaded c_einsum) at chi=%d, %d calls"
-                      % (chi_a, n),
-            "blas_fair": {"value": heff2_flops(chi_b) / tb * 1e-9, "unit": "GFLOP/s", "cores": os.cpu_count(),
-                          "sample": "same contractions via np.tensordot (threaded zgemm) at chi=%d, 1 call" % chi_b}}
+    plan = D.HeffPlan(D.C128, 4, chi, chi, [(ctx.dev(L), D.combine_twosite(W1, W2, np.complex128), ctx.dev(R))], ctx.ws)
+    xd = ctx.dev(x.reshape(-1)); yd = torch.empty_like(xd)
+    plan.apply(xd, yd, -1.0)
+    err = float(np.linalg.norm(yd.cpu().numpy() - ref) / np.linalg.norm(ref))
+    plan.close()
+    return {"value": heff2_flops(chi) / nslab / ta * 1e-9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+            "sample": "reference-faithful two-site Hfun (np.einsum, no optimize: single-threaded c_einsum) at chi=%d on %d slabs of "
+                      "%d right-bond rows (1/%d of every stage each)" % (chi, n, rows, nslab),
+            "parity_rel_err": err, "parity_what": "GPU mat-vec vs oracle (BLAS mode) on the same seeded chi=%d operands" % chi,
+            "blas_fair": {"value": heff2_flops(chi) / tb * 1e-9, "unit": "GFLOP/s", "cores": os.cpu_count(),
+                          "sample": "same contractions via np.tensordot (threaded zgemm) at chi=%d, 1 full call" % chi}}
 
 
-def scan_sample():
-    """s-points/hour on one GPU from a bounded sample of BASELINE configs[3] (ASEP N=50, chi=256 two-site,
-    64 s-values in [-0.5, 0.5]): four points spread over the range (the cost of a point varies 3x with s: the
-    s = -0.5 end needs ~22k mat-vecs, the middle ~4.5k), each cold-started through a [16, 64] chi ramp."""
+def small_chi_matvec(reps=30):
+    """The mat-vec where configs[1] and [3] live (chi = 256, 512; Heisenberg f64 w=5 and ASEP c128 w=6): ms, executed GEMM
+    TFLOP/s of the two GEMM launches (CUDA events, pdmrg_heff_apply_timed) and of the whole mat-vec."""
+    import torch
+    from pydmrg_b200 import core, device as D, mpo as M
+    out = {}
+    for tag, code, dt, mk in (("heisenberg_f64", D.F64, torch.float64, lambda: M.heisenberg_mpo(6)),
+                              ("asep_c128", D.C128, torch.complex128, lambda: M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)))):
+        ctx = core.Context("f64" if code == D.F64 else "c128")
+        W1, W2 = mk()[0][2:4]
+        w = W1.shape[0]
+        for chi in (128, 256, 512):
+            Wc = D.combine_twosite(W1, W2, D.np_dtype(code))
+            g = torch.Generator(device="cuda"); g.manual_seed(5)
+            rnd = lambda *s: torch.randn(*s, dtype=dt, device="cuda", generator=g)
+            L, R, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(4 * chi * chi)
+            y = torch.empty_like(x)
+            plan = D.HeffPlan(code, 4, chi, chi, [(L, Wc, R)], ctx.ws)
+            for _ in range(5):
+                plan.apply(x, y)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(reps):
+                plan.apply(x, y)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            st = np.zeros(3)
+            for _ in range(5):
+                st += np.array(plan.apply_timed(x, y))
+            st /= 5
+            out["%s_chi%d" % (tag, chi)] = {"ms": ms, "stage_ms": [float(v) for v in st],
+                                            "executed_gemm_tflops_whole_matvec": plan.flops_gemm / (ms * 1e-3) * 1e-12,
+                                            "executed_gemm_tflops_gemm_launches": plan.flops_gemm / ((st[0] + st[2]) * 1e-3) * 1e-12}
+            plan.close()
+    return out
+
+
+SCAN_PRM = (0.5, 0.5, 0.1, 0.9, 0.5, 0.5)
+
+
+def scan_sample(idx=(0, 16, 31, 32, 48, 63)):
+    """s-points/hour on one GPU from a bounded sample of BASELINE configs[3] (ASEP N=50, chi=256 two-site, 64 s-values in
+    [-0.5, 0.5]): six points INCLUDING the two next to s = 0, where the gap of the tilted generator closes and a point
+    costs an order of magnitude more mat-vecs than elsewhere (round 1 sampled four easy points).  Each cold-started
+    through a [16, 64] chi ramp.  Mean over the sample, not an extrapolation of the best case."""
     import torch
     from pydmrg_b200 import mpo as M, scan
-    idx = [0, 21, 42, 63]
+    idx = list(idx)
     s_vals = np.linspace(-0.5, 0.5, 64)[idx]
-    mpo_of = lambda s: M.asep_mpo(50, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    mpo_of = lambda s: M.asep_mpo(50, SCAN_PRM + (float(s),))
     np.random.seed(0)
+    st = {}
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = scan.run_scan(mpo_of, s_vals, 256, maxIter=3, tol=1e-8)
+    res = scan.run_scan(mpo_of, s_vals, 256, maxIter=3, tol=1e-8, stats=st)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     per = float(np.mean(res["sec"]))
     return {"config": "ASEP N=50 chi=256 two-site, points %s of 64 s-values, each cold through a [16,64] chi ramp, tol 1e-8" % idx,
             "s": [float(v) for v in s_vals], "sec_per_point": res["sec"], "s_points_per_hour_per_gpu": 3600.0 / per,
+            "n_matvec": st.get("n_matvec"), "cycles": st.get("cycles"),
             "E": [float(np.real(e)) for e in res["E"]], "E_imag_max": float(np.max(np.abs(np.imag(res["E"]))))}
+
+
+def scan_multi(points, rank, world, dist):
+    """configs[3] over the ranks: ``points`` of the 64 s-values (evenly spread), dynamic scheduling (scan.run_scan
+    schedule='dynamic': a rank takes the next point when it is free), no data-path collective."""
+    import torch
+    from pydmrg_b200 import mpo as M, scan
+    idx = [int(round(v)) for v in np.linspace(0, 63, points)]
+    s_vals = np.linspace(-0.5, 0.5, 64)[idx]
+    mpo_of = lambda s: M.asep_mpo(50, SCAN_PRM + (float(s),))
+    scan.run_scan(lambda s: M.asep_mpo(8, SCAN_PRM + (float(s),)), s_vals[:1], 16, ramp=(4,), maxIter=0)      # start-up
+    np.random.seed(0)
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    order = [int(i) for i in np.argsort(np.abs(s_vals), kind="stable")]          # the gap closes at s = 0: those points first
+    res = scan.run_scan(mpo_of, s_vals, 256, rank, world, dist, maxIter=3, tol=1e-8, schedule="dynamic", order=order)
+    torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"points": points, "wall_sec": float(t.item()), "s_points_per_hour": points / float(t.item()) * 3600.0,
+            "points_done_by_this_rank": len(res["points"]), "E_real": [float(np.real(e)) for e in res["E"]]}
 
 
 def full_sweep(args, ctx, shard=None, gauge_shortcut=False):
@@ -591,25 +722,38 @@ def full_sweep(args, ctx, shard=None, gauge_shortcut=False):
     extra = {} if shard is None else {"shard": shard}
     if gauge_shortcut:
         extra["gauge_shortcut"] = True
-    dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=True, ctx=ctx, **extra)
+    ramp_stats = {}
+    ramp_out = dmrg.run_dmrg(mpo, mbd=sched, tol=1e-9, maxIter=1, fname=os.path.join(tmp, "st"), twoSite=True, ctx=ctx, stats=ramp_stats,
+                             **extra)
     mpsL, _ = mps_tools.load_mps(os.path.join(tmp, "st_mbd%d" % (len(sched) - 1)))
     mpsL = [[ctx.dev(t) for t in mpsL[0]]]
     F = env.calc_env(mpsL[0], mpo, chi, gaugeSite=0, ctx=ctx)
     torch.cuda.synchronize()
     ramp = time.perf_counter() - t0
-    cache, secs, bonds, E, EE, stats = {}, [], [], None, None, {}
+    cache, secs, bonds, mvs, prof, E, EE, stats = {}, [], [], [], [], None, None, {}
     for _ in range(5):
         stats = {}
         torch.cuda.synchronize(); t0 = time.perf_counter()
         E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, chi, ctx=ctx, stats=stats, recycle=cache, **extra)
         torch.cuda.synchronize(); secs.append(time.perf_counter() - t0)
         bonds.append(int(max(t.shape[2] for t in mpsL[0])))
+        mvs.append(int(stats.get("n_matvec", 0)))
+    full = [i for i, b in enumerate(bonds) if b >= chi]
+    first_full = full[1] if len(full) > 1 else (full[0] if full else len(secs) - 1)   # first sweep that STARTS at full size
+    nb = 2 * (N - 1)
     return {"value": secs[-1], "unit": "s", "sweeps_sec": secs, "max_bond_after_sweep": bonds, "ramp_sec": ramp,
-            "E": [float(np.real(E)), float(np.imag(E))], "EE": float(EE), "n_matvec": stats.get("n_matvec"),
-            "bonds": 2 * (N - 1), "n_recycled": stats.get("n_recycled", 0), "n_exact_trunc": stats.get("n_exact_trunc", 0),
+            "first_full_size_sweep_sec": secs[first_full], "converged_sweep_sec": secs[-1],
+            "n_matvec_per_sweep": mvs, "matvecs_per_bond_per_sweep": [round(m / nb, 2) for m in mvs],
+            "E": [float(np.real(E)), float(np.imag(E))], "EE": float(EE),
+            "E_ramp_stages": [float(np.real(e)) for e in np.atleast_1d(ramp_out[0])], "EE_ramp_stages": [float(np.real(e)) for e in np.atleast_1d(ramp_out[1])],
+            "ramp_n_matvec": ramp_stats.get("n_matvec"),
+            "n_matvec": stats.get("n_matvec"), "bonds": nb, "n_recycled": stats.get("n_recycled", 0),
+            "n_exact_trunc": stats.get("n_exact_trunc", 0), "n_recycle_rejected": stats.get("n_recycle_rejected", 0),
+            "disc_max": stats.get("disc_max"),
             "n_sharded_solves": stats.get("n_sharded_solves", 0), "n_sharded_env": stats.get("n_sharded_env", 0),
             "n_gauge_moves": stats.get("n_gauge_moves", 0),
-            "how": "measured: TASEP N=%d chi=%d c128 two-site sweeps after a %s ramp" % (N, chi, sched)}
+            "how": "measured: TASEP s=+0.5 (entangled, EE ~ 0.83) N=%d chi=%d c128 two-site sweeps after a %s ramp; value = last sweep"
+                   % (N, chi, sched)}
 
 
 if __name__ == "__main__":

@@ -66,6 +66,12 @@ int pdmrg_gemm_nt_batched2(int dtype, int M, int N, int K, int nb1, int nb2, con
                            double alpha_re, double alpha_im, int beta, void* stream);
 /* force the 128- or 64-row CTA tile (0 = automatic wave-quantisation model); testing only */
 void pdmrg_set_force_tile_rows(int bm);
+/* Stream-K scheduling of the tile kernel (csrc/gemm_nt.cu): 0 = never, 1 = by the cost model (default: problems whose
+ * whole tiles fill the SMs badly, i.e. bond dimensions <= 512), 2 = whenever possible (tests).  The result does not
+ * depend on the mode beyond rounding (fixed summation order: deterministic).  pdmrg_last_gemm_streamk(): whether the
+ * last pdmrg_gemm_nt* launch used it. */
+void pdmrg_set_streamk_mode(int mode);
+int pdmrg_last_gemm_streamk(void);
 
 /* ---- strided 4-index copy:  out[i0,i1,i2,i3] (C-order, dims n0..n3) = f(in[sum i_k*s_k])
  * f = conj if conj != 0; if scale != NULL the element is multiplied by the REAL vector
@@ -243,6 +249,22 @@ int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* L_host_ptrs
                            double* e_out_host, void* vecs_out, long long vecs_stride,
                            int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
                            const void* diag, double pc_floor);
+/* The same loop with the solver options that go beyond the reference's algorithm (all opt-in; csrc/davidson.cu):
+ *   restart_keep > 0 : thick restart -- at a restart the basis is compressed to an orthonormal basis of the
+ *                      restart_keep lowest Ritz vectors (XS' = XS Q, AX' = AX Q, no new mat-vec) instead of being thrown
+ *                      away as la_tools.py:544-546 does; XS / AX then need max_space + 4*nroots + restart_keep rows;
+ *   tol_relative     : res_tol is relative to |theta| (ARPACK's rule; scipy eigs(tol=1e-5), tools/diag_tools.py:225);
+ *   diag             : optional diagonal preconditioner as in pdmrg_davidson_precond (NULL = the reference's identity).
+ * With the identity preconditioner the subspace is the Krylov space of the start vector, so restart_keep > 0 is
+ * thick-restarted Arnoldi (Krylov-Schur): the device-resident counterpart of calc_eigs_arnoldi (diag_tools.py:214-241). */
+int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs, double sign,
+                      int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots, int max_space,
+                      double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                      void* XS, void* AX, void* Rv, long long stride,
+                      void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
+                      double* e_out_host, void* vecs_out, long long vecs_stride,
+                      int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
+                      const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out);
 /* r <- r / (diag - theta) element-wise with the floor above; norm2_dev[0] = ||r||^2 of the result.  scratch as for the
  * other vector kernels (pdmrg_vec_scratch_bytes). */
 int pdmrg_vec_precond(int dtype, long long n, void* r, const void* diag, double theta_re, double theta_im,

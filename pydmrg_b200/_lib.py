@@ -37,6 +37,8 @@ def _load():
         "pdmrg_gemm_nt": (i, [i, i, i, i, i, vp, ll, ll, vp, ll, ll, i, vp, ll, ll, d, d, i, vp]),
         "pdmrg_gemm_nt_batched2": (i, [i, i, i, i, i, i, POINTER(i), vp, ll, ll, ll, vp, ll, ll, ll, i, vp, ll, ll, ll, d, d, i, vp]),
         "pdmrg_set_force_tile_rows": (None, [i]),
+        "pdmrg_set_streamk_mode": (None, [i]),
+        "pdmrg_last_gemm_streamk": (i, []),
         "pdmrg_permute4": (i, [i, vp, vp, i, i, i, i, ll, ll, ll, ll, i, vp, i, vp]),
         "pdmrg_heff_plan_create": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp)]),
         "pdmrg_heff_plan_create_sharded": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp)]),
@@ -76,6 +78,8 @@ def _load():
                                POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp]),
         "pdmrg_davidson_precond": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
                                        vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d]),
+        "pdmrg_davidson_ex": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
+                                  vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d, i, i, POINTER(i)]),
         "pdmrg_vec_precond": (i, [i, ll, vp, vp, d, d, d, vp, vp, sz, vp]),
         "pdmrg_heff_diag": (i, [i, i, i, i, i, i, vp, vp, vp, d, i, vp, vp]),
         "pdmrg_host_eig": (i, [i, POINTER(d), POINTER(d), POINTER(d)]),

@@ -32,7 +32,7 @@ def parse_dtype(dtype):
 class Context:
     """dtype + device + scratch for one calculation."""
 
-    def __init__(self, dtype="c128", device=None, svd_method="auto"):
+    def __init__(self, dtype="c128", device=None, svd_method="auto", projective_min=128):
         self.code = parse_dtype(dtype)
         if not torch.cuda.is_available():
             raise RuntimeError("pydmrg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -44,6 +44,10 @@ class Context:
         self.svd_ws = D.Workspace(self.device)
         # 'auto': cuSOLVER gesvd for small cuts, the Gram/eigh/QR route (5-8x faster) from 128 up
         self.svd_method = {"gesvd": D.SVD_GESVD, "gesvdj": D.SVD_GESVDJ, "gram": D.SVD_GRAM, "auto": -1}[svd_method]
+        # finite two-site sweeps: cuts of at least this size take the projective / warm-started truncation
+        # (truncate.truncate_twosite), smaller ones a full cuSOLVER SVD (cheaper there); tests lower it to put the
+        # projective path in a heavily truncating regime that a dense oracle can afford
+        self.projective_min = int(projective_min)
 
     def svd_method_for(self, rows, cols):
         if self.svd_method >= 0:

@@ -194,9 +194,11 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
                          void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
                          double* e_out_host, void* vecs_out, long long vecs_stride,
                          int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
-                         const void* diag, double pc_floor) {
+                         const void* diag, double pc_floor, int restart_keep = 0, int tol_relative = 0,
+                         int* n_restarts_out = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(plan != nullptr, "pdmrg_davidson: null plan");
+  PDMRG_REQUIRE(restart_keep >= 0 && restart_keep <= 16, "pdmrg_davidson: restart_keep must be in 0..16");
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "pdmrg_davidson: bad dtype");
   PDMRG_REQUIRE(nroots >= 1 && nroots <= 4 && nx0 >= 1 && nx0 <= nroots, "pdmrg_davidson: 1..4 roots, at most one guess per root");
   PDMRG_REQUIRE(scratch_bytes >= pdmrg_davidson_scratch_bytes(nroots, max_space), "pdmrg_davidson: scratch too small");
@@ -218,7 +220,9 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
   auto rv = [&](int i) { return Rv + (size_t)E * i * stride; };
   double* pin = g_pin.get((size_t)2 * rows * (nroots + 2) * 2 + 64);
   PDMRG_REQUIRE(pin != nullptr, "pdmrg_davidson: pinned staging allocation failed");
-  const double thresh2 = res_tol >= 0 ? res_tol * res_tol : lindep;
+  double thresh2 = res_tol >= 0 ? res_tol * res_tol : lindep;
+  const bool thick = restart_keep > 0;
+  int n_restarts = 0;
 
   auto normalise_from = [&](double* vec, double* n2slot) -> int {   // vec <- vec / sqrt(n2slot[0])
     return pdmrg_vec_normalize(dtype, n, vec, n2slot, vec, stream);
@@ -305,8 +309,12 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
         e[k] = cd(e[k].real(), 0.0);
       }
     }
+    if (tol_relative && res_tol >= 0) {                                     // ARPACK's criterion: ||r|| <= tol * |theta|
+      const double sc = std::max(std::abs(e[0]), 2.220446049250313e-16);
+      thresh2 = res_tol * res_tol * sc * sc;
+    }
     // residuals, their projection against the basis and both norms, without a host round trip in between
-    coef.resize((size_t)2 * space);
+    coef.resize((size_t)2 * std::max(space, rows));
     for (int k = 0; k < nr; ++k) {
       for (int i = 0; i < space; ++i) {
         if (cplx) { coef[2 * i] = vsel[(size_t)k * rows + i].real(); coef[2 * i + 1] = vsel[(size_t)k * rows + i].imag(); }
@@ -343,6 +351,85 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
     if (keep.empty()) { ++cyc; break; }                                     // la_tools.py:539-541
     if (fixed_cycles > 0 && cyc + 1 >= fixed_cycles) { ++cyc; break; }
     fresh = space + nroots > ms;                                            // la_tools.py:544
+    if (fresh && thick) {
+      // Thick restart (Krylov-Schur style; opt-in, the reference restarts from the nroots Ritz vectors alone): the
+      // basis is compressed to an orthonormal basis Q of the span of the kk lowest Ritz vectors,
+      //   XS' = XS Q,  AX' = AX Q (no new mat-vec),  H' = Q^H H Q,
+      // and the iteration goes on with the residual direction of THIS cycle, which is orthogonal to span(XS)
+      // and therefore to XS'.  Nearly degenerate partners of the wanted state survive the restart, which is what
+      // makes the restarted iteration converge when the gap to the second state closes (s -> 0 in the s-ensemble).
+      int kk = std::min(std::max(restart_keep, nr), space - 1);
+      std::vector<cd> Q((size_t)space * kk);
+      int got = 0;
+      for (int c = 0; c < space && got < kk; ++c) {
+        const int src = order[c];
+        if (!cplx && std::abs(w[src].imag()) > 1e-9 * std::max(1.0, std::abs(w[src].real()))) continue;   // f64: real pairs only
+        cd* q = &Q[(size_t)got * space];
+        if (c < nr) for (int i = 0; i < space; ++i) q[i] = vsel[(size_t)c * rows + i];                    // phase-fixed copies
+        else for (int i = 0; i < space; ++i) q[i] = vv[(size_t)src * space + i];
+        if (!cplx && c >= nr) {
+          int piv = 0;
+          for (int i = 1; i < space; ++i) if (std::abs(q[i]) > std::abs(q[piv])) piv = i;
+          const cd ph = std::conj(q[piv]) / std::abs(q[piv]);
+          for (int i = 0; i < space; ++i) q[i] = cd((q[i] * ph).real(), 0.0);
+        }
+        bool ok = true;
+        for (int pass = 0; pass < 2 && ok; ++pass) {                        // modified Gram-Schmidt, twice
+          for (int j = 0; j < got; ++j) {
+            const cd* qj = &Q[(size_t)j * space];
+            cd d = 0;
+            for (int i = 0; i < space; ++i) d += std::conj(qj[i]) * q[i];
+            for (int i = 0; i < space; ++i) q[i] -= d * qj[i];
+          }
+          double nn = 0;
+          for (int i = 0; i < space; ++i) nn += std::norm(q[i]);
+          if (nn < 1e-20) { ok = false; break; }
+          nn = 1.0 / std::sqrt(nn);
+          for (int i = 0; i < space; ++i) q[i] *= nn;
+        }
+        if (ok) ++got;
+      }
+      kk = got;
+      if (kk >= nr) {
+        for (int j = 0; j < kk; ++j) {
+          for (int i = 0; i < space; ++i) {
+            if (cplx) { coef[2 * i] = Q[(size_t)j * space + i].real(); coef[2 * i + 1] = Q[(size_t)j * space + i].imag(); }
+            else coef[i] = Q[(size_t)j * space + i].real();
+          }
+          if (pdmrg_vec_combine(dtype, n, space, coef.data(), XS, stride, xs(space + j), 0, stream)) return 1;
+          if (pdmrg_vec_combine(dtype, n, space, coef.data(), AX, stride, ax(space + j), 0, stream)) return 1;
+        }
+        for (int j = 0; j < kk; ++j) {
+          PDMRG_CHECK_CUDA(cudaMemcpyAsync(xs(j), xs(space + j), (size_t)n * eb, cudaMemcpyDeviceToDevice, stream));
+          PDMRG_CHECK_CUDA(cudaMemcpyAsync(ax(j), ax(space + j), (size_t)n * eb, cudaMemcpyDeviceToDevice, stream));
+        }
+        std::vector<cd> HQ((size_t)space * kk, cd(0)), Hn((size_t)kk * kk, cd(0));
+        for (int j = 0; j < kk; ++j)
+          for (int i = 0; i < space; ++i) {
+            cd sacc = 0;
+            for (int l = 0; l < space; ++l) sacc += H(i, l) * Q[(size_t)j * space + l];
+            HQ[(size_t)j * space + i] = sacc;
+          }
+        for (int j = 0; j < kk; ++j)
+          for (int i = 0; i < kk; ++i) {
+            cd sacc = 0;
+            for (int l = 0; l < space; ++l) sacc += std::conj(Q[(size_t)i * space + l]) * HQ[(size_t)j * space + l];
+            Hn[(size_t)j * kk + i] = sacc;
+          }
+        for (int j = 0; j < rows; ++j) for (int i = 0; i < rows; ++i) H(i, j) = 0.0;
+        for (int j = 0; j < kk; ++j) for (int i = 0; i < kk; ++i) H(i, j) = Hn[(size_t)j * kk + i];
+        // the Ritz coefficients of the wanted states in the NEW basis (needed if the loop ends before the next solve)
+        for (int k = 0; k < nr; ++k) {
+          std::vector<cd> vn(kk, cd(0));
+          for (int j = 0; j < kk; ++j)
+            for (int l = 0; l < space; ++l) vn[j] += std::conj(Q[(size_t)j * space + l]) * vsel[(size_t)k * rows + l];
+          for (int i = 0; i < rows; ++i) vsel[(size_t)k * rows + i] = i < kk ? vn[i] : cd(0);
+        }
+        space = kk;
+        fresh = false;
+        ++n_restarts;
+      }
+    }
     if (!fresh) {
       for (int k : keep) {
         // a single new direction is normalised straight into its basis slot (no copy next cycle)
@@ -374,6 +461,7 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
     e_out_host[2 * k + 1] = e[k].imag();
   }
   if (n_matvec_out) *n_matvec_out = n_mv;
+  if (n_restarts_out) *n_restarts_out = n_restarts;
   if (cycles_out) *cycles_out = cyc;
   if (last_res_out) *last_res_out = last_res;
   return 0;
@@ -403,4 +491,27 @@ extern "C" int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* 
   return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
                        fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
                        vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor);
+}
+
+// The same loop with the solver options that go beyond the reference's algorithm (all opt-in):
+//   restart_keep > 0 : thick restart -- the basis is compressed to the restart_keep lowest Ritz vectors instead of
+//                      being thrown away (XS / AX need max_space + 4*nroots + restart_keep rows);
+//   tol_relative     : res_tol is relative to |theta| (ARPACK's stopping rule, scipy eigs(tol=...), diag_tools.py:225);
+//   diag (optional)  : diagonal preconditioner as in pdmrg_davidson_precond.
+// With the identity preconditioner the expansion vectors are residuals, i.e. the subspace is the Krylov space of the
+// start vector: restart_keep > 0 then IS thick-restarted Arnoldi (Krylov-Schur), the device-resident counterpart of the
+// reference's ARPACK path (calc_eigs_arnoldi, diag_tools.py:214-241).
+extern "C" int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* Ls, const void* const* Rs, double sign,
+                                 int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots,
+                                 int max_space, double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                                 void* XS_, void* AX_, void* Rv_, long long stride,
+                                 void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
+                                 double* e_out_host, void* vecs_out, long long vecs_stride,
+                                 int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
+                                 const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out) {
+  PDMRG_REQUIRE(diag == nullptr || pc_floor > 0.0, "pdmrg_davidson_ex: the preconditioner needs a positive floor");
+  return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
+                       fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
+                       vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor, restart_keep,
+                       tol_relative, n_restarts_out);
 }

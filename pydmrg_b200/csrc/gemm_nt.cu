@@ -21,6 +21,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <map>
+#include <mutex>
+
 namespace pdmrg {
 namespace {
 
@@ -55,6 +58,15 @@ struct GemmParams {
   // accum2: the nb2 entries of the second batch level are SUMMED into one output tile (the k-loop runs over
   // all of them) instead of producing nb2 separate outputs -- a long-K product whose K is not contiguous
   int accum2;
+  // stream-K (small problems: fewer tiles than ~4 waves): the global iteration space (tiles x k-iterations) is cut into
+  // gridDim.x equal contiguous ranges; a tile split between CTAs is finished by the CTA that holds its FIRST k-segment
+  // (its last work item), which adds the fragment-layout partials the other holders left in `sk_partial` (fixed order:
+  // deterministic).  sk_flags[c] == sk_epoch announces the partial of CTA c.
+  int streamk;
+  long long sk_per;          // k-iterations per CTA
+  double* sk_partial;        // gridDim.x x (MI*8*256) doubles
+  unsigned int* sk_flags;
+  unsigned int sk_epoch;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -94,6 +106,40 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Work items of one CTA: (tile, [k0, k1)) in processing order.  Data-parallel mode: whole tiles, strided over the grid.
+// Stream-K mode: CTA c owns the contiguous range r = gridDim.x-1-c of the global iteration space (reversed, so that the
+// finisher of a split tile only ever waits for CTAs with a LOWER index, which the hardware dispatches first).
+struct WorkIter {
+  int mode, total_tiles, ktot, tile, step;
+  long long it, it_end;
+  __device__ WorkIter(const GemmParams& p, int total_tiles_, int ktot_) : mode(p.streamk), total_tiles(total_tiles_), ktot(ktot_) {
+    if (mode) {
+      const long long total = (long long)total_tiles * ktot;
+      const long long r = (long long)gridDim.x - 1 - blockIdx.x;
+      it = r * p.sk_per;
+      it_end = it + p.sk_per < total ? it + p.sk_per : total;
+    } else {
+      tile = blockIdx.x;
+      step = gridDim.x;
+    }
+  }
+  __device__ bool next(int& t, int& k0, int& k1) {
+    if (mode) {
+      if (it >= it_end) return false;
+      t = (int)(it / ktot);
+      k0 = (int)(it - (long long)t * ktot);
+      const long long room = it_end - it;
+      k1 = (long long)(ktot - k0) <= room ? ktot : (int)(k0 + room);
+      it += k1 - k0;
+      return true;
+    }
+    if (tile >= total_tiles) return false;
+    t = tile; k0 = 0; k1 = ktot;
+    tile += step;
+    return true;
+  }
+};
+
 template <bool CPLX, int MI, bool SCATTER = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -129,7 +175,10 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ktot_p = p.kiters * nb2_k;
+      WorkIter wi(p, total_tiles, ktot_p);
+      int tile, k0, k1;
+      while (wi.next(tile, k0, k1)) {
         const int tm = tile % p.tiles_m;
         const int rest = tile / p.tiles_m;
         const int tn = rest % p.tiles_n;
@@ -137,18 +186,17 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rowA = tm * BM, rowB = tn * B_ROWS;
         const int b1 = b / nb2_out;
         const int a1 = p.bcastA1 ? 0 : b1, c1 = p.bcastB1 ? 0 : b1;
-        for (int q = 0; q < nb2_k; ++q) {
+        for (int kglob = k0; kglob < k1; ++kglob) {
+          const int q = kglob / p.kiters, kit = kglob - q * p.kiters;
           const int b2 = p.idx2[p.accum2 ? q : b % p.nb2];
           const int a2 = p.bcastA2 ? 0 : b2, c2 = p.bcastB2 ? 0 : b2;
-          for (int kit = 0; kit < p.kiters; ++kit) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t full = full0 + 8 * stage;
-            mbar_expect_tx(full, TX_BYTES);
-            const uint32_t sA = smem_base + stage * STAGE_BYTES;
-            tma_load_4d(sA, &tmA, kit * BK, rowA, a2, a1, full);
-            tma_load_4d(sA + A_BYTES, &tmB, kit * BK, rowB, c2, c1, full);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t full = full0 + 8 * stage;
+          mbar_expect_tx(full, TX_BYTES);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          tma_load_4d(sA, &tmA, kit * BK, rowA, a2, a1, full);
+          tma_load_4d(sA + A_BYTES, &tmB, kit * BK, rowB, c2, c1, full);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -176,7 +224,10 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  const int ktot = p.kiters * nb2_k;
+  WorkIter wi(p, total_tiles, ktot);
+  int tile, seg_k0, seg_k1;
+  while (wi.next(tile, seg_k0, seg_k1)) {
     const int tm = tile % p.tiles_m;
     const int rest = tile / p.tiles_m;
     const int tn = rest % p.tiles_n;
@@ -188,8 +239,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    const int ktot = p.kiters * nb2_k;
-    for (int kit = 0; kit < ktot; ++kit) {
+    for (int kit = seg_k0; kit < seg_k1; ++kit) {
       mbar_wait(full0 + 8 * stage, phase);
       const unsigned char* sA = smem + stage * STAGE_BYTES;
       const unsigned char* sB = sA + A_BYTES;
@@ -222,6 +272,47 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    if (!SCATTER && p.streamk && !(seg_k0 == 0 && seg_k1 == ktot)) {
+      constexpr int FRAG = MI * 8;                               // accumulator doubles per thread
+      const int ctid = threadIdx.x;                              // consumer thread id, 0..255
+      if (seg_k0 != 0) {
+        // END / middle segment: leave the partial in fragment layout and announce it
+        double* dst = p.sk_partial + (size_t)blockIdx.x * (FRAG * 256) + ctid;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __stcg(dst + ((i * 4 + j) * 2 + 0) * 256, acc[i][j][0]);
+            __stcg(dst + ((i * 4 + j) * 2 + 1) * 256, acc[i][j][1]);
+          }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ctid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(p.sk_epoch) : "memory");
+        continue;
+      }
+      // START segment: this CTA finishes the tile.  The remaining segments [seg_k1, ktot) belong to the ranges
+      // r+1, r+2, ... = CTAs blockIdx.x-1, blockIdx.x-2, ... (all dispatched before this one); add them in order.
+      int have = seg_k1;
+      for (int c = (int)blockIdx.x - 1; have < ktot; --c) {
+        if (ctid == 0) {
+          unsigned int v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.sk_flags + c) : "memory");
+          } while (v != p.sk_epoch);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const double* src = p.sk_partial + (size_t)c * (FRAG * 256) + ctid;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j][0] += __ldcg(src + ((i * 4 + j) * 2 + 0) * 256);
+            acc[i][j][1] += __ldcg(src + ((i * 4 + j) * 2 + 1) * 256);
+          }
+        have += (int)((long long)(ktot - have) < p.sk_per ? (ktot - have) : p.sk_per);
+      }
     }
 
     // ------------------------------ epilogue ----------------------------------------
@@ -406,12 +497,44 @@ int choose_bm(long long M, long long tiles_n, long long nbatch) {
   return c64 < c128 ? 64 : 128;
 }
 
+// ---- stream-K scratch: one set of partial-tile buffers + flags per CUDA stream (launches on one stream are ordered;
+// concurrent streams must not share partials).  Allocated on first use, kept for the life of the process.
+struct StreamKScratch {
+  double* partial = nullptr;
+  unsigned int* flags = nullptr;
+  unsigned int epoch = 0;
+};
+std::mutex g_sk_mutex;
+std::map<std::pair<int, cudaStream_t>, StreamKScratch> g_sk_scratch;
+std::atomic<int> g_streamk_mode{1};     // 0 = never, 1 = cost model, 2 = always (tests)
+std::atomic<int> g_last_streamk{0};
+
+int streamk_scratch(cudaStream_t stream, StreamKScratch* out) {
+  int dev = 0;
+  PDMRG_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_sk_mutex);
+  StreamKScratch& sc = g_sk_scratch[std::make_pair(dev, stream)];
+  if (!sc.partial) {
+    const size_t ctas = (size_t)num_sms();
+    PDMRG_CHECK_CUDA(cudaMalloc(&sc.partial, ctas * 8 * 8 * 256 * sizeof(double)));
+    PDMRG_CHECK_CUDA(cudaMalloc(&sc.flags, ctas * sizeof(unsigned int)));
+    PDMRG_CHECK_CUDA(cudaMemset(sc.flags, 0, ctas * sizeof(unsigned int)));      // legacy-stream memset: ordered before any launch
+    PDMRG_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  sc.epoch += 1;
+  if (sc.epoch == 0) sc.epoch = 1;
+  *out = sc;
+  return 0;
+}
+
 }  // namespace
 }  // namespace pdmrg
 
 using namespace pdmrg;
 
 extern "C" int pdmrg_last_gemm_path(void) { return g_last_path.load(); }
+extern "C" void pdmrg_set_streamk_mode(int mode) { g_streamk_mode.store(mode); }
+extern "C" int pdmrg_last_gemm_streamk(void) { return g_last_streamk.load(); }
 extern "C" void pdmrg_set_force_generic_gemm(int on) { g_force_generic.store(on); }
 extern "C" void pdmrg_set_force_tile_rows(int bm) { g_force_bm.store(bm); }
 
@@ -504,14 +627,40 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
     const int bn = cplx ? BNR / 2 : BNR;
     p.kiters = (int)((kreal + BK - 1) / BK);
     p.tiles_n = (N + bn - 1) / bn;
-    const int bm = choose_bm(M, p.tiles_n, nbatch);
+    int bm = choose_bm(M, p.tiles_n, nbatch);
+    // stream-K when whole tiles quantise badly over the SMs (bond dimensions <= 512: a fraction of a wave to a few
+    // waves): cost in k-iterations of the busiest SM, data-parallel = ceil(tiles / SMs) * ktot (x 0.52 for the 64-row
+    // tile), stream-K = ceil(tiles * ktot / SMs) + ~3 for the partial store / fix-up
+    p.streamk = 0; p.sk_per = 0; p.sk_partial = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
+    int grid_sk = 0;
+    {
+      const long long sms = num_sms();
+      const long long ktot = (long long)p.kiters * (accum2 ? nb2 : 1);
+      const long long t128 = ((M + 127) / 128) * (long long)p.tiles_n * nbatch, t64 = ((M + 63) / 64) * (long long)p.tiles_n * nbatch;
+      const double dp = bm == 128 ? (double)((t128 + sms - 1) / sms) * ktot : (double)((t64 + sms - 1) / sms) * ktot * 0.52;
+      const long long iters = t128 * ktot;
+      const double sk = (double)((iters + sms - 1) / sms) + 3.0;
+      const int mode = g_streamk_mode.load();
+      if (!scatter && mode != 0 && iters >= 8 && ktot >= 2 && (mode == 2 || (sk < 0.9 * dp && t128 < 6 * sms))) {
+        long long g = sms < iters / 4 ? sms : iters / 4;
+        if (g < 1) g = 1;
+        const long long per = (iters + g - 1) / g;
+        g = (iters + per - 1) / per;
+        StreamKScratch sc;
+        if (streamk_scratch(stream, &sc)) return 1;
+        bm = 128;
+        p.streamk = 1; p.sk_per = per; p.sk_partial = sc.partial; p.sk_flags = sc.flags; p.sk_epoch = sc.epoch;
+        grid_sk = (int)g;
+      }
+    }
+    g_last_streamk.store(p.streamk);
     p.tiles_m = (M + bm - 1) / bm;
     CUtensorMap tmA, tmB;
     if (make_map(&tmA, A, kreal, M, lda * E, p.bcastA2 ? 1 : max2 + 1, strideA2 * E, p.bcastA1 ? 1 : nb1, strideA1 * E, bm)) return 1;
     if (make_map(&tmB, B, kreal, N, ldb * E, p.bcastB2 ? 1 : max2 + 1, strideB2 * E, p.bcastB1 ? 1 : nb1, strideB1 * E, bn)) return 1;
     const long long total = (long long)p.tiles_m * p.tiles_n * nbatch;
     PDMRG_REQUIRE(total < (1ll << 31), "pdmrg_gemm_nt: too many tiles");
-    const int grid = (int)(total < num_sms() ? total : num_sms());
+    const int grid = p.streamk ? grid_sk : (int)(total < num_sms() ? total : num_sms());
     if (scatter) {
       static bool attr2 = false;
       if (!attr2) {
@@ -545,6 +694,8 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
   dim3 grid((N + 31) / 32, (M + 31) / 32, (unsigned)nbatch);
   PDMRG_REQUIRE(grid.y <= 65535 && nbatch <= 65535, "pdmrg_gemm_nt: generic path extent too large");
   p.kiters = 0; p.tiles_m = p.tiles_n = 0;
+  p.streamk = 0; p.sk_per = 0; p.sk_partial = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
+  g_last_streamk.store(0);
   if (cplx)
     gemm_nt_generic_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, (const double*)A, lda, strideA1, strideA2, (const double*)B, ldb,
                                                            strideB1, strideB2, conjB, (double*)C, ldc, strideC1, strideC2,

@@ -96,11 +96,12 @@ def _orthonormalise(ops, src, dst, norm_slot, small):
 
 
 def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
-                    res_tol=None, fixed_cycles=None, stats=None, sign=-1.0, diag=None, precond_floor=0.1):
+                    res_tol=None, fixed_cycles=None, stats=None, sign=-1.0, diag=None, precond_floor=0.1,
+                    restart_keep=0, tol_relative=False):
     """The same solver sequenced in C++ (csrc/davidson.cu, ``pdmrg_davidson``): one C-ABI call per
     local eigenproblem, operator = ``sign`` * H_eff of ``plan``."""
     ms = max_space + 3 * nroots
-    rows = ms + nroots
+    rows = ms + nroots + int(restart_keep)
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
     for k, g in enumerate(x0):
         W.R[nroots + k][:n].copy_(g)
@@ -113,7 +114,11 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
             int(max_cycle), int(fixed_cycles or 0), D._ptr(W.XS), D._ptr(W.AX), D._ptr(W.R),
             W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
             e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), D._stream())
-    if diag is None:
+    n_rs = ctypes.c_int(0)
+    if restart_keep or tol_relative:
+        check(lib.pdmrg_davidson_ex(*args, D._ptr(diag), float(precond_floor), int(restart_keep), int(bool(tol_relative)),
+                                    ctypes.byref(n_rs)), "pdmrg_davidson_ex")
+    elif diag is None:
         check(lib.pdmrg_davidson(*args), "pdmrg_davidson")
     else:
         check(lib.pdmrg_davidson_precond(*args, D._ptr(diag), float(precond_floor)), "pdmrg_davidson_precond")
@@ -124,12 +129,14 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
         stats["n_matvec"] = stats.get("n_matvec", 0) + n_mv.value
         stats["cycles"] = stats.get("cycles", 0) + cyc.value
         stats["last_residual"] = last.value
+        if restart_keep:
+            stats["n_thick_restarts"] = stats.get("n_thick_restarts", 0) + n_rs.value
     return e, [out[k] for k in range(nr)]
 
 
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
              res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None, diag=None,
-             precond_floor=0.1):
+             precond_floor=0.1, restart_keep=0, tol_relative=False):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
@@ -141,6 +148,12 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     ``diag``: diagonal of the operator (device vector) -- switches the correction step from the reference's identity
     preconditioner (diag_tools.py:137-139) to t = r / (diag - theta), |diag - theta| >= precond_floor (absolute):
     same eigenpairs, fewer cycles in cold sweeps; opt-in because the iteration counts then differ from the reference.
+    ``restart_keep`` > 0: thick restart -- at a restart (la_tools.py:544) the basis is compressed to an orthonormal basis
+    of that many lowest Ritz vectors (XS <- XS Q, AX <- AX Q, projected matrix Q^H H Q; no new mat-vec) and the iteration
+    continues with the current residual direction, instead of starting again from the Ritz vectors alone.  Nearly
+    degenerate partners of the target survive the restart: orders of magnitude fewer mat-vecs when the gap closes (scan
+    points next to s = 0).  With the identity preconditioner this is thick-restarted Arnoldi (Krylov-Schur).
+    ``tol_relative``: ``res_tol`` is relative to |theta| (ARPACK's stopping rule).
     ``consensus``: optional callable applied to the small device arrays right before the host reads them
     (sharded sweeps: a broadcast from rank 0, so that every rank takes the same control decisions and the
     collectives inside ``matvec`` stay matched whatever the last bit of a reduction does).
@@ -152,9 +165,9 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
         native = os.environ.get("PDMRG_PY_DAVIDSON", "0") != "1"
     if native and plan is not None and nroots <= 4 and len(x0) <= nroots and n > nroots:
         return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats,
-                               diag=diag, precond_floor=precond_floor)
+                               diag=diag, precond_floor=precond_floor, restart_keep=restart_keep, tol_relative=tol_relative)
     max_space = max_space + 3 * nroots
-    rows = max_space + nroots
+    rows = max_space + nroots + int(restart_keep)
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
     ops = W.ops(n)
     XS, AX = W.XS[:, :n], W.AX[:, :n]
@@ -205,6 +218,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
         if code == D.F64:
             e, v = _force_real(e, v)
         nr = e.shape[0]
+        if tol_relative and res_tol is not None:
+            thresh2 = (res_tol * max(abs(e[0]), 2.3e-16)) ** 2
         # residual r_k = sum_i v_ik (A xs_i - e_k xs_i) and its norm (la_tools.py:479-482), then --
         # with no host round trip in between -- projection against the basis and the new norm
         for k in range(nr):
@@ -239,6 +254,33 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
         if fixed_cycles is not None and cyc + 1 >= fixed_cycles:
             break
         fresh = space + nroots > max_space                         # la_tools.py:544
+        if fresh and restart_keep:
+            # thick restart: keep an orthonormal basis Q of the lowest Ritz vectors (see csrc/davidson.cu)
+            kk = min(max(int(restart_keep), nr), space - 1)
+            Y = np.concatenate([v, vv[:, nr:]], axis=1)
+            if code == D.F64:
+                wall = w
+                cols = [c for c in range(Y.shape[1]) if c < nr or abs(wall[c].imag) <= 1e-9 * max(1.0, abs(wall[c].real))]
+                Y = Y[:, cols]
+                piv = np.argmax(np.abs(Y), axis=0)
+                ph = Y[piv, np.arange(Y.shape[1])]
+                Y = np.real(Y * (np.conj(ph) / np.abs(ph))).astype(np.complex128)
+            Q = np.linalg.qr(Y[:, :kk])[0]
+            kk = Q.shape[1]
+            if kk >= nr:
+                for j in range(kk):
+                    ops.combine(Q[:, j], W.XS, space, XS[space + j])
+                    ops.combine(Q[:, j], W.AX, space, AX[space + j])
+                for j in range(kk):
+                    XS[j].copy_(XS[space + j]); AX[j].copy_(AX[space + j])
+                Hn = Q.conj().T @ heff[:space, :space] @ Q
+                v = Q.conj().T @ v
+                heff[:] = 0
+                heff[:kk, :kk] = Hn
+                space = kk
+                fresh = False
+                if stats is not None:
+                    stats["n_thick_restarts"] = stats.get("n_thick_restarts", 0) + 1
         if fresh:
             x0 = [W.R[nr + k][:n] for k in range(nr)]
             for k in range(nr):

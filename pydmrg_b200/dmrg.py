@@ -382,7 +382,8 @@ def run_sweeps(mpsL, W, F, initGuess=None, maxIter=0, minIter=None, tol=1e-10, f
 def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, maxIter=10, minIter=0, fname=None,
              nStates=1, targetState=0, constant_mbd=False, alg="davidson", preserveState=False,
              gaugeSiteSave=None, returnState=False, returnEnv=False, returnEntSpec=False, orthonormalize=False,
-             calcLeftState=False, *, dtype="c128", twoSite=False, ctx=None, stats=None, pad_bonds=None, **solver):
+             calcLeftState=False, *, dtype="c128", twoSite=False, ctx=None, stats=None, pad_bonds=None, name_suffix="",
+             **solver):
     """Same call signature and return packing as pydmrg/dmrg.py:309-315 / :491-508.
     Keyword-only extensions: ``dtype`` ('c128' as the reference, or 'f64' for real problems),
     ``twoSite`` (two-site SVD sweeps), ``stats`` (dict: mat-vec / cycle counters), solver
@@ -390,7 +391,11 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
     whether a state carried to a larger ``mbd`` is zero-padded to it first (mps_tools.py:244-279).
     One-site sweeps cannot grow a bond, so they always pad (the reference's behaviour); two-site sweeps
     grow every bond by up to a factor d per visit on their own, so by default they do NOT pad -- the
-    first sweeps of a chi stage then run on the small tensors instead of on zero-filled large ones."""
+    first sweeps of a chi stage then run on the small tensors instead of on zero-filled large ones.
+    ``name_suffix``: appended AFTER the ``_mbd{i}`` part of every state file read or written (``'_left'`` lets a run
+    on ``mpo_conj_trans(mpo)`` use the reference's names for the left eigenstate, dmrg.py:423,436,476).
+    An in-memory ``initGuess`` seeds the first ``mbd`` stage only; later stages continue from the previous stage's
+    state (the in-memory equivalent of the reference's save / load / increase_all_mbd between stages)."""
     ctx = ctx or default_context(dtype)
     N = len(mpo[0])
     if pad_bonds is None:
@@ -417,10 +422,10 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
         # ---- initial MPS (dmrg.py:350-389) ----------------------------------------------
         if initGuess is None:
             if mbdInd != 0 and fname is not None:
-                mpsList, gSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1))
+                mpsList, gSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1) + name_suffix)
                 mpsList = grow(mpsList, mbdi)
                 if calcLeftState:
-                    mpslList, glSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1) + "_left")
+                    mpslList, glSite = mps_tools.load_mps(fname + "_mbd" + str(mbdInd - 1) + name_suffix + "_left")
                     mpslList = grow(mpslList, mbdi)
             else:
                 mpsList = mps_tools.make_all_mps_right(mps_tools.create_all_mps(N, mbdi, nStates))
@@ -431,13 +436,21 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
                     glSite = 0
         elif isinstance(initGuess, str):
             idx = mbdInd if mbdInd == 0 else mbdInd - 1
-            mpsList, gSite = mps_tools.load_mps(initGuess + "_mbd" + str(idx))
+            mpsList, gSite = mps_tools.load_mps(initGuess + "_mbd" + str(idx) + name_suffix)
             if calcLeftState:
-                mpslList, glSite = mps_tools.load_mps(initGuess + "_mbd" + str(idx) + "_left")
+                mpslList, glSite = mps_tools.load_mps(initGuess + "_mbd" + str(idx) + name_suffix + "_left")
             if mbdInd != 0:
                 mpsList = grow(mpsList, mbdi)
                 if calcLeftState:
                     mpslList = grow(mpslList, mbdi)
+        elif mbdInd != 0:
+            # in-memory guess: it seeded stage 0; this stage continues from the previous stage's result, whose
+            # centre sits where run_sweeps left it (site 0 after two-site sweeps, gaugeSiteSave after one-site ones)
+            gSite = 0 if twoSite else gaugeSiteSave
+            mpsList = grow([[Context.host(t) for t in M] for M in mpsList], mbdi)
+            if calcLeftState:
+                glSite = gSite
+                mpslList = grow([[Context.host(t) for t in M] for M in mpslList], mbdi)
         else:
             # an in-memory mpsList (lists of ndarrays), gauge at site 0 -- or (mpsList, gaugeSite)
             guess, gSite = (initGuess if (isinstance(initGuess, tuple) and len(initGuess) == 2
@@ -452,6 +465,17 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
         if calcLeftState:
             glSite = int(glSite)
             mpslList = [[ctx.dev(t) for t in M] for M in mpslList]
+        if twoSite:
+            # two-site sweeps start at bond (0, 1): a state whose centre is elsewhere (a one-site checkpoint saved at
+            # N//2+1, the reference's default, or initGuess=(mps, g)) is re-gauged to site 0 first -- otherwise the
+            # blocks F[1..g] built by calc_env(gaugeSite=g) are LEFT blocks where the sweep expects right ones
+            from .gauge import move_gauge
+            if gSite != 0:
+                mpsList = [move_gauge(M, gSite, 0, ctx=ctx) for M in mpsList]
+                gSite = 0
+            if calcLeftState and glSite != 0:
+                mpslList = [move_gauge(M, glSite, 0, ctx=ctx) for M in mpslList]
+                glSite = 0
         # ---- environment (dmrg.py:391-397) ----------------------------------------------
         if initEnv is None:
             env = calc_env(mpsList[0], mpo, mbdi, gaugeSite=gSite, ctx=ctx)
@@ -461,7 +485,7 @@ def run_dmrg(mpo, initEnv=None, initGuess=None, mbd=[2, 4, 8, 16], tol=1e-5, max
             env = initEnv
             if calcLeftState:
                 env, envl = initEnv[0], initEnv[1]
-        fname_mbd = None if fname is None else fname + "_mbd" + str(mbdInd)
+        fname_mbd = None if fname is None else fname + "_mbd" + str(mbdInd) + name_suffix
         common = dict(maxIter=maxIter[mbdInd], minIter=minIter[mbdInd], tol=tol[mbdInd], nStates=nStates, alg=alg,
                       targetState=targetState, gaugeSiteSave=gaugeSiteSave, preserveState=preserveState,
                       returnState=True, returnEnv=True, returnEntSpec=True, orthonormalize=orthonormalize,

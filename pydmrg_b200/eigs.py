@@ -66,11 +66,28 @@ def make_ham_func(M, W, F, site, usePrecond=False, debug=False, oneSite=True, ct
     ctx = ctx or default_context()
     plan, shape = make_plan(M, W, F, site, oneSite, ctx)
 
+    stage = {}
+
     def Hfun(x):
-        xd = ctx.dev(x).reshape(-1)
-        yd = torch.empty_like(xd)
-        plan.apply(xd, yd, -1.0)
-        return like(yd, x)
+        if is_dev(x):
+            xd = ctx.dev(x).reshape(-1)
+            yd = torch.empty_like(xd)
+            plan.apply(xd, yd, -1.0)
+            return yd
+        # host vector in, host vector out (the reference's contract).  The device buffers are kept by the closure; the
+        # result is a FRESH ndarray on page-locked memory from torch's caching host allocator (solvers keep every image
+        # they are handed, so a staging buffer must never be reused) -- D2H at link speed and no extra host copy.  A
+        # page-locked input (e.g. a vector this closure returned) goes up asynchronously as well.
+        xh = torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1), dtype=ctx.npdtype))
+        if "x" not in stage:
+            stage["x"] = torch.empty(plan.n, dtype=ctx.tdtype, device=ctx.device)
+            stage["y"] = torch.empty_like(stage["x"])
+        stage["x"].copy_(xh, non_blocking=True)
+        plan.apply(stage["x"], stage["y"], -1.0)
+        yh = torch.empty(plan.n, dtype=ctx.tdtype, pin_memory=True)
+        yh.copy_(stage["y"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return yh.numpy()
 
     def precond(dx, e, x0):                                   # diag_tools.py:137-139 (identity)
         return dx
@@ -116,7 +133,7 @@ def check_overlap(guess, vecs, E, preserveState, ctx):
 def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
               orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
               fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000, shard=None, max_space=12,
-              precond=None, precond_floor=0.1):
+              precond=None, precond_floor=0.1, restart_keep=0, arnoldi_tol=1e-5):
     """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
     array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise.
 
@@ -125,7 +142,15 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     mat-vec).  The Davidson control scalars and the final eigenvectors are taken from rank 0, so the ranks
     cannot drift apart.  ``max_space``: Davidson subspace before a restart (la_tools.py:318 default 12, widened by
     3 per root, :412); a larger one trades vector passes for fewer mat-vecs in cold sweeps.  ``precond='diag'``:
-    diagonal Davidson preconditioner built from diag(H_eff) (davidson.davidson) instead of the reference's identity."""
+    diagonal Davidson preconditioner built from diag(H_eff) (davidson.davidson) instead of the reference's identity.
+    ``restart_keep`` > 0: thick restart of the Davidson subspace (davidson.davidson).
+
+    ``alg='arnoldi'`` (calc_eigs_arnoldi, diag_tools.py:214-241: ARPACK ``eigs(k=nStates, which='SR', tol=1e-5, v0=guess)``)
+    runs DEVICE-RESIDENT thick-restarted Arnoldi: the same Krylov kernels and C++ loop with the identity preconditioner
+    (expansion by residuals = the Krylov space of v0), ARPACK's subspace size ncv = max(2k+1, 20), a thick restart that keeps
+    the wanted + k + 2 Ritz vectors (Krylov-Schur, mathematically the implicit restart ARPACK performs) and ARPACK's
+    relative stopping rule ||r|| <= tol |theta|.  ``alg='arnoldi_host'`` keeps SciPy's ARPACK on the host driving the device
+    mat-vec (one D2H + H2D of the vector per mat-vec) for cross-checks."""
     ctx = ctx or default_context()
     own_plan = plan is None
     sharded = None
@@ -153,21 +178,28 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
             shard.consensus(gk)
         vals, vecs = davidson(lambda x, y: sharded.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=None,
-                              native=False, max_cycle=max_cycle, consensus=shard.consensus, max_space=max_space, **pc)
+                              native=False, max_cycle=max_cycle, consensus=shard.consensus, max_space=max_space,
+                              restart_keep=restart_keep, **pc)
         E = -vals
         if stats is not None:
             stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
     elif alg == "davidson":
         vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=plan,
-                              native=native, max_cycle=max_cycle, max_space=max_space, **pc)
+                              native=native, max_cycle=max_cycle, max_space=max_space, restart_keep=restart_keep, **pc)
         E = -vals                                               # diag_tools.py:265,273
     elif alg == "exact":
         E, vecs = _eigs_exact(plan, n, nS, ctx)
     elif alg == "arnoldi":
+        ncv = max(2 * nS + 1, 20)                               # scipy.sparse.linalg.eigs default
+        vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses[:1] if nS == 1 else guesses, n, ctx.code, ctx.device,
+                              nroots=nS, lindep=lindep, res_tol=arnoldi_tol, tol_relative=True, stats=stats, plan=plan, native=native,
+                              max_cycle=max_cycle, max_space=max(ncv - 3 * nS, nS + 2), restart_keep=min(2 * nS + 2, ncv - nS - 1))
+        E = -vals
+    elif alg == "arnoldi_host":
         E, vecs = _eigs_arnoldi(plan, n, nS, guesses[0], ctx)
     else:
-        raise ValueError("alg must be 'davidson', 'exact' or 'arnoldi'")
+        raise ValueError("alg must be 'davidson', 'exact', 'arnoldi' or 'arnoldi_host'")
     if shard is not None and shard.world > 1:
         # EVERY solve of a sharded run -- also the small bonds every rank solves on its own -- ends with rank 0's
         # eigenpairs on all ranks: a rounding difference that flips one convergence test would otherwise leave the

@@ -44,6 +44,51 @@ def gather_scan(local_values, n_points, rank, world, dist=None, interleave=False
     return torch.view_as_complex(t.cpu()).numpy()
 
 
+class WorkQueue:
+    """Dynamic distribution of independent scan points: ``order`` (the same list on every rank, most expensive
+    first if known) is handed out one point at a time -- a rank takes the next point when it is free.  The only shared
+    state is ONE atomic counter in torch.distributed's key-value store (``Store.add``, served by rank 0's TCPStore: a
+    few bytes per point, nothing on the data path).  The cost of a scan point varies by more than 10x (the gap of the
+    tilted generator closes at s = 0), which static blocks or strides cannot balance."""
+
+    _calls = 0
+
+    def __init__(self, order, rank, world, dist=None, store=None):
+        self.order, self.rank, self.world = list(order), rank, world
+        WorkQueue._calls += 1                                    # every rank builds its queues in the same order
+        self.key = "pdmrg_workqueue_%d" % WorkQueue._calls
+        self.local = 0
+        self.store = None
+        if world > 1:
+            self.store = store if store is not None else dist.distributed_c10d._get_default_store()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.store is None:
+            pos = self.local
+            self.local += 1
+        else:
+            pos = int(self.store.add(self.key, 1)) - 1
+        if pos >= len(self.order):
+            raise StopIteration
+        return self.order[pos]
+
+
+def gather_scan_dynamic(indices, local_values, n_points, world, dist=None):
+    """Full result array on every rank from (index, value) pairs held by the ranks (one object gather at the end)."""
+    out = np.zeros(n_points, dtype=np.complex128)
+    pairs = [(int(i), complex(v)) for i, v in zip(indices, local_values)]
+    if world > 1 and dist is not None:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, pairs)
+        pairs = [p for sub in everyone for p in sub]
+    for i, v in pairs:
+        out[i] = v
+    return out
+
+
 def run_dmrg_left_right(mpo, rank, world, dist, runner=None, **kwargs):
     """``run_dmrg(..., calcLeftState=True)`` with the right and the left eigenstate computed on different
     ranks.  The reference runs them one after the other as two independent DMRGs -- the
@@ -74,9 +119,9 @@ def run_dmrg_left_right(mpo, rank, world, dist, runner=None, **kwargs):
         elif _is_pair(v):
             kw[key] = v[side]
     if side == 1:
-        for key in ("fname", "initGuess"):
-            if isinstance(kw.get(key), str):
-                kw[key] = kw[key] + "_left"
+        # the left rank reads / writes '<name>_mbd{i}_left', the reference's names (dmrg.py:423,436,476) and those of
+        # run_dmrg(calcLeftState=True), so checkpoints are interchangeable between the drivers
+        kw["name_suffix"] = kw.get("name_suffix", "") + "_left"
     out = None
     if rank < 2:                                                 # ranks beyond the first pair have nothing to do
         out = runner(mpo if side == 0 else mpo_conj_trans(mpo), **kw)

@@ -14,11 +14,12 @@ import time
 import numpy as np
 
 from . import mpo as mpo_lib
-from .parallel import gather_scan, scan_indices
+from .parallel import WorkQueue, gather_scan, gather_scan_dynamic, scan_indices
 
 
 def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
-             twoSite=True, dtype="c128", continuation=False, ramp_res_tol=1e-5, stats=None, **solver):
+             twoSite=True, dtype="c128", continuation=False, ramp_res_tol=1e-5, stats=None, schedule="static", order=None,
+             **solver):
     """Run ``run_dmrg(mpo_of(v), mbd=...)`` for every v in ``values`` (this rank's block only).
 
     Every point cold-starts through the chi ramp by default: the ramp stages run one sweep with a
@@ -33,15 +34,28 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     per bond in the ramp was tried and rejected (the final stage then needs 15-40x more mat-vecs and can
     settle on the wrong branch of the non-Hermitian generator).
 
+    ``schedule='dynamic'`` (cold starts only): the points are not dealt out in advance; a rank takes the next point of
+    ``order`` (default: as given; pass the expected-most-expensive first) whenever it is free (parallel.WorkQueue: one
+    atomic counter in the process group's store, nothing on the data path).
+
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
     rank's points, points: their indices)."""
     from .dmrg import run_dmrg
     n = len(values)
     interleave = not continuation          # cold starts: every world-th point (balanced); continuation: blocks
-    mine = scan_indices(n, rank, world, interleave)
+    dynamic = schedule == "dynamic" and not continuation
+    if schedule not in ("static", "dynamic"):
+        raise ValueError("schedule must be 'static' or 'dynamic'")
+    if dynamic:
+        todo = WorkQueue(list(range(n)) if order is None else [int(i) for i in order], rank, world, dist)
+        mine = []
+    else:
+        todo = mine = scan_indices(n, rank, world, interleave)
     E_loc, EE_loc, secs = [], [], []
     prev = None
-    for idx in mine:
+    for idx in todo:
+        if dynamic:
+            mine.append(idx)
         mpo = mpo_of(values[idx])
         t0 = time.perf_counter()
         if prev is None or not continuation:
@@ -55,13 +69,18 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
                     opts["res_tol"] = ramp_res_tol
                 out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
                                initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **opts)
-                guess = out[-1] if twoSite else _grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd]))
+                # one-site runs leave the centre at gaugeSiteSave = N//2+1 (dmrg.py:322), two-site ones at site 0
+                guess = out[-1] if twoSite else (_grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd])),
+                                                 len(mpo[0]) // 2 + 1)
         else:
             out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,
                            dtype=dtype, returnState=True, stats=stats, **solver)
         secs.append(time.perf_counter() - t0)
         E_loc.append(out[0]); EE_loc.append(out[1])
-        prev = out[-1]
+        prev = out[-1] if twoSite else (out[-1], len(mpo[0]) // 2 + 1)
+    if dynamic:
+        return {"E": gather_scan_dynamic(mine, E_loc, n, world, dist), "EE": gather_scan_dynamic(mine, EE_loc, n, world, dist),
+                "sec": secs, "points": mine}
     return {"E": gather_scan(E_loc, n, rank, world, dist, interleave), "EE": gather_scan(EE_loc, n, rank, world, dist, interleave),
             "sec": secs, "points": mine}
 
@@ -86,6 +105,8 @@ def main():
                     help="give every local rank its own slice of the host cores (the scan is host-latency bound)")
     ap.add_argument("--precond", default=None, choices=[None, "diag"], help="Davidson preconditioner (default: the reference's identity)")
     ap.add_argument("--max-space", type=int, default=12, help="Davidson subspace before a restart (reference: 12)")
+    ap.add_argument("--schedule", default="dynamic", choices=["static", "dynamic"],
+                    help="dynamic: a rank takes the next point when it is free, points nearest s = 0 (the expensive ones) first")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.pin_cores and hasattr(os, "sched_setaffinity"):
@@ -117,8 +138,9 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     stats = {}
+    order = [int(i) for i in np.argsort(np.abs(s_vals), kind="stable")]        # the gap closes at s = 0: those points first
     res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter, stats=stats,
-                   precond=args.precond, max_space=args.max_space)
+                   precond=args.precond, max_space=args.max_space, schedule=args.schedule, order=order)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     per_rank = [{"rank": rank, "sec": round(sum(res["sec"]), 3), "points": len(res["points"]), "cycles": stats.get("cycles"),
                  "n_matvec": stats.get("n_matvec")}]
@@ -133,7 +155,7 @@ def main():
         print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
                           "host_cores": os.cpu_count(), "cores_per_rank": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
                           "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt, "per_rank": per_rank,
-                          "precond": args.precond, "max_space": args.max_space, "blas_threads_per_rank": blas_threads,
+                          "precond": args.precond, "max_space": args.max_space, "schedule": args.schedule, "blas_threads_per_rank": blas_threads,
                           "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
     if world > 1:
         dist.destroy_process_group()

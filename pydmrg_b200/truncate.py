@@ -90,6 +90,16 @@ def recycle_allowed(cache, site, shape_key):
     return st["disc"] < RECYCLE_SAFE_DISCARD or st["exact_visits"] >= 2
 
 
+def recycled_weight_ok(cache, site, disc_now):
+    """After a warm-started step: the weight it discarded must not exceed what the bond's last exact decomposition
+    discarded by more than a factor 2 (+1e-13 of rounding) -- a state that moved between two visits can leave the
+    carried subspace suboptimal without any sign in the orthogonality defect; the caller then redoes the bond exactly."""
+    st = cache.get(("state", site))
+    if st is None:
+        return True
+    return disc_now <= 2.0 * st["disc"] + 1e-13
+
+
 def note_exact_visit(cache, site, shape_key, disc):
     st = cache.get(("state", site))
     if st is None or st["shape"] != shape_key:
@@ -151,7 +161,7 @@ def eig_truncate(psi, shape, mbd, ctx, direction, spare=0, extras=None):
     return A, B, Sn, EE, EEs
 
 
-def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext, method=None):
+def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext, method=None, weight_check=None):
     """Projective truncation warm-started from the bond's previous bases (csrc/solver.cu
     pdmrg_recycle_basis; same outputs as eig_truncate plus the new spare rows, or None when it cannot be
     used).  ``warm`` is the site tensor holding the previous basis of the side that is NOT being left
@@ -182,6 +192,12 @@ def recycled_truncate(psi, shape, mbd, ctx, direction, warm, ext, method=None):
     if not ok:
         return None
     EE, EEs, Sn = calc_entanglement(Sh[:k])
+    if weight_check is not None:
+        # captured weight = sum of the squared row norms of the new centre / ||psi||^2 (exact for any rotation of the rows)
+        tot = float(torch.linalg.vector_norm(psi).item()) ** 2
+        disc = max(0.0, 1.0 - float(np.dot(Sh[:k], Sh[:k])) / tot) if tot > 0 else 0.0
+        if not weight_check(disc):
+            return None
     A = ctx.empty(d1, Dl, k)
     B = ctx.empty(d2, k, Dr)
     if right:
@@ -258,7 +274,7 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
     (used at the bond whose spectrum is reported)."""
     d1, d2, Dl, Dr = shape
     rows, cols = Dl * d1, d2 * Dr
-    if not (ctx.svd_method < 0 and min(rows, cols) >= 128):
+    if not (ctx.svd_method < 0 and min(rows, cols) >= getattr(ctx, "projective_min", 128)):
         return svd_truncate(psi, shape, mbd, ctx, absorb=direction)
     if recycle is None:
         return eig_truncate(psi, shape, mbd, ctx, direction)
@@ -281,7 +297,10 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
         if is_dev(top) and tuple(top.shape) == want and top.dtype == ctx.tdtype and ext.dtype == ctx.tdtype \
                 and tuple(ext.shape) == (p, cols if right else rows):
             # a bond where the Cholesky-QR2 variant had to be redone with Householder QR keeps using the latter
-            r = recycled_truncate(psi, shape, mbd, ctx, direction, top.contiguous(), ext, method=recycle.get(("qr", site)))
+            r = recycled_truncate(psi, shape, mbd, ctx, direction, top.contiguous(), ext, method=recycle.get(("qr", site)),
+                                  weight_check=lambda disc: recycled_weight_ok(recycle, site, disc))
+            if r is None and stats is not None:
+                stats["n_recycle_rejected"] = stats.get("n_recycle_rejected", 0) + 1
             if r is not None:
                 recycle[(site, other)] = r[5]
                 if r[6] == D.RECYCLE_HOUSEHOLDER:
@@ -300,6 +319,7 @@ def truncate_twosite(psi, shape, mbd, ctx, direction, recycle=None, site=None, w
         recycle.pop((site, other), None)
     if stats is not None:
         stats["n_exact_trunc"] = stats.get("n_exact_trunc", 0) + 1
+        stats["disc_max"] = max(stats.get("disc_max", 0.0), extras.get("disc", 0.0))     # largest discarded weight seen
     return out
 
 
@@ -388,9 +408,10 @@ def renorm_inf(mpsList, mpoList, envList, vecs, mbd, ctx=None):
 # one-site reduced-density-matrix route
 # ---------------------------------------------------------------------------------------
 def _spectrum_from_rdm(w, keep):
-    """Schmidt spectrum of the cut from RDM eigenvalues (ascending from heevd): the reference takes
-    the singular values of the whole (d*Dl, Dr) matrix (dmrg.py:30-37), i.e. sqrt of every eigenvalue."""
-    lam = np.clip(w[::-1], 0.0, None)                           # descending, >= 0
+    """Schmidt spectrum of the cut from RDM eigenvalues (ascending from heevd): the reference takes the
+    min(d*Dl, Dr) singular values of the (d*Dl, Dr) matrix (dmrg.py:30-37) = sqrt of the ``keep`` largest RDM
+    eigenvalues (the remaining d*Dl - keep are zero up to rounding and are not part of its spectrum)."""
+    lam = np.clip(w[::-1][:keep], 0.0, None)                    # descending, >= 0
     return calc_entanglement(np.sqrt(lam))
 
 

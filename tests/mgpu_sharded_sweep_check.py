@@ -3,7 +3,7 @@ ranks (run_dmrg(..., shard=ShardSpec)) against the same sweeps run unsharded on 
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_sharded_sweep_check.py
 
-PENDING: written after the round-1 GPU budget was spent; first run is item 2 of tools/round2_validate.sh.
+First GPU runs: round 2 (profiles/sharded_sweep_r02_n2.txt, _n8.txt).
 Environment: PDMRG_CHECK_CHI (default 64), PDMRG_CHECK_N (default 16), PDMRG_CHECK_TIMING=1 adds a chi=1024
 timing of one converged sweep sharded vs unsharded (TASEP N=100, BASELINE configs[2])."""
 import json
@@ -36,7 +36,7 @@ def main():
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         dist.init_process_group("nccl")
     from pydmrg_b200 import dmrg, mpo as M, parallel
-    chi = int(os.environ.get("PDMRG_CHECK_CHI", "64"))
+    chi = int(os.environ.get("PDMRG_CHECK_CHI", str(max(64, 16 * world))))      # ShardSpec needs 16 ket columns per rank
     N = int(os.environ.get("PDMRG_CHECK_N", "16"))
     ok = True
     report = {"world": world, "chi": chi, "N": N}

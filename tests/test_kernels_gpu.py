@@ -52,6 +52,68 @@ def test_gemm_nt_shapes(D, cplx, shape):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(256, 1024, 256, 5), (128, 128, 64, 1), (130, 70, 33, 3), (256, 192, 1000, 1), (512, 2048, 512, 2),
+                                   (129, 257, 130, 1), (200, 64, 8, 7), (1024, 1024, 96, 1)])
+def test_gemm_nt_stream_k(D, cplx, shape):
+    """Stream-K scheduling (tiles split between CTAs along K, partials added by the finisher in a fixed order): same
+    numbers as the data-parallel schedule to rounding, bit-identical from run to run, with beta = 1, a batch level,
+    ragged extents and complex alpha."""
+    M, N, K, nb = shape
+    rng = np.random.default_rng(M + 3 * N + 7 * K + nb)
+    mk = (lambda *s: crand(rng, *s)) if cplx else (lambda *s: rng.standard_normal(s))
+    A, B, C0 = mk(nb, M, K), mk(nb, N, K), mk(nb, M, N)
+    alpha = (0.7 - 0.3j) if cplx else -1.3
+    ref = alpha * np.einsum("bmk,bnk->bmn", A, B) + C0
+    outs = []
+    for mode in (2, 2, 0):
+        D.lib.pdmrg_set_streamk_mode(mode)
+        try:
+            Cd = dev(C0)
+            D.gemm_nt(dev(A), dev(B), Cd, M=M, N=N, K=K, batch=nb, lda=K, ldb=K, ldc=N, strideA=M * K, strideB=N * K,
+                      strideC=M * N, alpha=alpha, beta=1)
+            used = D.lib.pdmrg_last_gemm_streamk()
+        finally:
+            D.lib.pdmrg_set_streamk_mode(1)
+        torch.cuda.synchronize()
+        assert used == (1 if mode == 2 else 0)
+        outs.append(Cd.cpu().numpy())
+        assert rel(outs[-1], ref) < TOL
+    assert np.array_equal(outs[0], outs[1])                     # deterministic summation order
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("chi", [64, 128, 256, 512])
+def test_heff_stream_k_matches_data_parallel(D, dtype, chi):
+    """The two-site mat-vec at the bond dimensions where the cost model switches stream-K on (configs[1], [3]) against the
+    same plan with stream-K disabled and against the oracle."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import core, mpo as M
+    ctx = core.Context(dtype)
+    cplx = dtype == "c128"
+    W1, W2 = (M.asep_mpo(6, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)) if cplx else M.heisenberg_mpo(6))[0][2:4]
+    w = W1.shape[0]
+    rng = np.random.default_rng(chi)
+    mk = (lambda *s: crand(rng, *s)) if cplx else (lambda *s: rng.standard_normal(s))
+    L, R, x = mk(chi, w, chi), mk(chi, w, chi), mk(2, 2, chi, chi)
+    plan = D.HeffPlan(ctx.code, 4, chi, chi, [(ctx.dev(L), D.combine_twosite(W1, W2, ctx.npdtype), ctx.dev(R))], ctx.ws)
+    xd = ctx.dev(x.reshape(-1))
+    ys = []
+    for mode in (1, 0):
+        D.lib.pdmrg_set_streamk_mode(mode)
+        try:
+            y = torch.empty_like(xd)
+            plan.apply(xd, y, -1.0)
+            torch.cuda.synchronize()
+        finally:
+            D.lib.pdmrg_set_streamk_mode(1)
+        ys.append(y.cpu().numpy())
+    ref = orc.heff_twosite(x.reshape(-1), [L], [W1], [W2], [R], x.shape, "blas")
+    if not cplx:
+        ref = ref.real
+    assert rel(ys[0], ref) < TOL and rel(ys[1], ref) < TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_gemm_nt_paths_agree(D, cplx):
     """TMA/DMMA path and the generic kernel give the same numbers; path selection is visible."""
     rng = np.random.default_rng(5)

@@ -88,6 +88,50 @@ def test_gather_scan_gloo_world2():
         assert np.array_equal(out, expect)
 
 
+def _queue_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import time
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pydmrg_b200.parallel import WorkQueue, gather_scan_dynamic
+    order = [5, 0, 3, 1, 4, 2, 6]
+    got = []
+    for idx in WorkQueue(order, rank, world, dist):
+        got.append(idx)
+        time.sleep(0.3 if (rank == 0 and len(got) == 1) else 0.01)      # rank 0's first point is an expensive one
+    out = gather_scan_dynamic(got, [complex(i, rank) for i in got], len(order), world, dist)
+    # a second queue in the same process group must start from a fresh counter
+    again = list(WorkQueue([0, 1], rank, world, dist))
+    dist.barrier()
+    q.put((rank, got, out, again))
+    dist.destroy_process_group()
+
+
+def test_dynamic_work_queue_gloo_world2():
+    """parallel.WorkQueue: every point is taken exactly once, in the given order, and the rank that sits on an
+    expensive point takes fewer of them; results are assembled on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_queue_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = {r: (got, out, again) for r, got, out, again in (q.get(timeout=120) for _ in ps)}
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res[0][0] + res[1][0]) == list(range(7))
+    assert len(res[0][0]) < len(res[1][0])
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(np.real(res[0][1]), np.arange(7))
+    assert sorted(res[0][2] + res[1][2]) == [0, 1]
+
+
+def test_work_queue_single_process():
+    from pydmrg_b200.parallel import WorkQueue
+    assert list(WorkQueue([2, 0, 1], 0, 1)) == [2, 0, 1]
+
+
 # ---------------------------------------------------------------------------------------
 # right / left eigenstates on different ranks (SURVEY 8e row 2)
 # ---------------------------------------------------------------------------------------
@@ -153,6 +197,26 @@ def test_left_right_eigenstates_on_two_ranks_gloo():
     den = orc.full_contract(None, mr[0], lmps)
     assert abs(num / den - E) < 1e-7 * abs(E)
     assert abs(left[0] - np.conj(right[0])) < 1e-7 * abs(E)
+
+
+def test_left_rank_uses_the_reference_file_names(tmp_path):
+    """The left rank of run_dmrg_left_right reads / writes '<name>_mbd{i}_left' (dmrg.py:423,436,476): the names of the
+    reference and of run_dmrg(calcLeftState=True), not '<name>_left_mbd{i}'."""
+    from pydmrg_b200.parallel import run_dmrg_left_right
+    seen = {}
+
+    class FakeDist:
+        @staticmethod
+        def all_gather_object(out, obj):
+            out[0] = out[1] = obj
+
+    def runner(mpo, **kw):
+        seen.update(kw)
+        return [1.0, 0.0, None]
+
+    run_dmrg_left_right([[None]], 1, 2, FakeDist, runner=runner, fname=str(tmp_path / "st"), initGuess=str(tmp_path / "g"), mbd=4)
+    assert seen["fname"] == str(tmp_path / "st") and seen["initGuess"] == str(tmp_path / "g")
+    assert seen["name_suffix"] == "_left"
 
 
 def test_left_right_pair_detection():

@@ -39,7 +39,7 @@ def test_arnoldiCheck(E):
     np.random.seed(0)
     E1 = dmrg.run_dmrg(mpo, mbd=MBD, alg="exact", ctx=ctx, recycle=False)[0]
     np.random.seed(0)
-    E2 = dmrg.run_dmrg(mpo, mbd=MBD, alg="arnoldi", ctx=ctx, recycle=False)[0]
+    E2 = dmrg.run_dmrg(mpo, mbd=MBD, alg="arnoldi", ctx=ctx, recycle=False, native=False)[0]
     assert np.isclose(E1, E2, atol=1e-4, rtol=1e-4)
 
 

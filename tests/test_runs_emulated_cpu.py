@@ -441,3 +441,43 @@ def test_full_contract_with_orthonormalised_states(E, golden):
     ed = g["asep6_ed"]
     lo, hi = min(ed[0].real, ed[1].real), max(ed[0].real, ed[1].real)
     assert lo - 1e-6 < e0.real < hi + 1e-6 and lo - 1e-6 < e1.real < hi + 1e-6    # both live in the two-state span
+
+
+def test_two_site_resume_from_one_site_checkpoint(E, golden, tmp_path):
+    """A one-site checkpoint (centre saved at N//2+1, the reference's default gaugeSiteSave) resumed with twoSite=True,
+    and initGuess=(mps, g): the centre is moved to site 0 before the blocks are built, so the very first two-site
+    sweep already sits at the converged energy (maxIter=0: one sweep).  Before the fix the blocks F[1..g] were left
+    blocks used as right ones and the first sweep solved wrong local problems."""
+    from pydmrg_b200 import dmrg, mpo as M, mps as mps_tools
+    g = golden["runs"]
+    mpo = M.asep_mpo(6, tuple(float(v) for v in g["asep6_params"]))
+    ctx = E.Context("c128")
+    np.random.seed(3)
+    stem = str(tmp_path / "one")
+    E0, _, _, mps = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=6, ctx=ctx, native=False, res_tol=1e-11, fname=stem, returnState=True)
+    assert mps_tools.load_mps(stem + "_mbd0")[1] == 6 // 2 + 1
+    st = {}
+    E1 = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=0, ctx=ctx, native=False, res_tol=1e-11, initGuess=stem, twoSite=True, stats=st)[0]
+    assert abs(E1 - E0) < 1e-10 * abs(E0)
+    # a converged start costs about one mat-vec cycle per bond (2 x 5 bonds); wrong blocks cost hundreds
+    assert st["n_matvec"] <= 40, st["n_matvec"]
+    E2 = dmrg.run_dmrg(mpo, mbd=8, tol=1e-10, maxIter=0, ctx=ctx, native=False, res_tol=1e-11, initGuess=(mps, 4), twoSite=True)[0]
+    assert abs(E2 - E0) < 1e-10 * abs(E0)
+
+
+@pytest.mark.parametrize("twoSite", [False, True])
+def test_in_memory_guess_continues_through_the_chi_schedule(E, golden, twoSite):
+    """initGuess as an in-memory state with several mbd stages: stage k > 0 continues from stage k-1 (it used to
+    restart every stage from the original guess, so the schedule did no useful work)."""
+    from pydmrg_b200 import dmrg, mpo as M, mps as mps_tools
+    g = golden["runs"]
+    mpo = M.asep_mpo(6, tuple(float(v) for v in g["asep6_params"]))
+    ctx = E.Context("c128")
+    np.random.seed(5)
+    guess = mps_tools.make_all_mps_right(mps_tools.create_all_mps(6, 2, 1))
+    st = {}
+    Es = dmrg.run_dmrg(mpo, mbd=[2, 4, 8], tol=1e-10, maxIter=[4, 4, 0], ctx=ctx, native=False, res_tol=1e-11, initGuess=guess,
+                       twoSite=twoSite, stats=st)[0]
+    # the last stage runs ONE sweep only: it can only sit at the ED value if it started from the chi=4 result
+    assert abs(Es[2] - g["asep6_ed_top"]) < (1e-9 if twoSite else 1e-6) * abs(g["asep6_ed_top"])
+    assert Es[0].real <= Es[1].real + 1e-9 <= Es[2].real + 2e-9
