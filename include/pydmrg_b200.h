@@ -161,6 +161,16 @@ int pdmrg_heff_apply_fused_ket(pdmrg_heff_plan* plan, pdmrg_comm* comm, const vo
 int pdmrg_heff_plan_create_ketsplit(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
                                     const int* wL_host, const int* wR_host, const void* const* Wc_host,
                                     const unsigned char* const* block_mask_host, int k0, int klen);
+/* Plan creation WITHOUT any device allocation, legacy-stream copy or synchronisation (what a sweep uses: one plan per
+ * bond step, possibly several sweeps running concurrently on different streams of one GPU).  The host-side operator
+ * tables are built here; the caller then provides a device buffer of pdmrg_heff_plan_blob_bytes() bytes (256-byte
+ * aligned, alive until the last apply has run) and the stream on which the small H2D copy is ordered.
+ * block_mask_host may be NULL; k0 = 0, klen = -1 selects the whole left bond. */
+int pdmrg_heff_plan_create_host(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                const int* wL, const int* wR, const void* const* Wc_host,
+                                const unsigned char* const* block_mask_host, int k0, int klen);
+size_t pdmrg_heff_plan_blob_bytes(const pdmrg_heff_plan* plan);
+int pdmrg_heff_plan_upload(pdmrg_heff_plan* plan, void* blob_dev, size_t blob_bytes, void* stream);
 /* algorithmic FLOPs of one apply (dense-W count of SURVEY 8d) and with block sparsity */
 double pdmrg_heff_flops_dense(const pdmrg_heff_plan* plan);
 double pdmrg_heff_flops_sparse(const pdmrg_heff_plan* plan);
@@ -254,7 +264,9 @@ int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* L_host_ptrs
  *                      restart_keep lowest Ritz vectors (XS' = XS Q, AX' = AX Q, no new mat-vec) instead of being thrown
  *                      away as la_tools.py:544-546 does; XS / AX then need max_space + 4*nroots + restart_keep rows;
  *   tol_relative     : res_tol is relative to |theta| (ARPACK's rule; scipy eigs(tol=1e-5), tools/diag_tools.py:225);
- *   diag             : optional diagonal preconditioner as in pdmrg_davidson_precond (NULL = the reference's identity).
+ *   diag             : optional diagonal preconditioner as in pdmrg_davidson_precond (NULL = the reference's identity);
+ *   stagnation > 0   : stop a solve whose residual has not been halved within that many cycles (the reference goes on to
+ *                      max_cycle = 1000; nearly defective local problems next to s = 0 stall at ||r|| ~ 1e-4).
  * With the identity preconditioner the subspace is the Krylov space of the start vector, so restart_keep > 0 is
  * thick-restarted Arnoldi (Krylov-Schur): the device-resident counterpart of calc_eigs_arnoldi (diag_tools.py:214-241). */
 int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, const void* const* R_host_ptrs, double sign,
@@ -264,7 +276,8 @@ int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, con
                       void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
                       double* e_out_host, void* vecs_out, long long vecs_stride,
                       int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
-                      const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out);
+                      const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out,
+                      int stagnation);
 /* r <- r / (diag - theta) element-wise with the floor above; norm2_dev[0] = ||r||^2 of the result.  scratch as for the
  * other vector kernels (pdmrg_vec_scratch_bytes). */
 int pdmrg_vec_precond(int dtype, long long n, void* r, const void* diag, double theta_re, double theta_im,

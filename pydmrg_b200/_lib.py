@@ -43,6 +43,9 @@ def _load():
         "pdmrg_heff_plan_create": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp)]),
         "pdmrg_heff_plan_create_sharded": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp)]),
         "pdmrg_heff_plan_create_ketsplit": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), i, i]),
+        "pdmrg_heff_plan_create_host": (i, [POINTER(vp), i, i, i, i, i, POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), i, i]),
+        "pdmrg_heff_plan_blob_bytes": (sz, [vp]),
+        "pdmrg_heff_plan_upload": (i, [vp, vp, sz, vp]),
         "pdmrg_heff_plan_destroy": (None, [vp]),
         "pdmrg_heff_workspace_bytes": (sz, [vp]),
         "pdmrg_heff_apply": (i, [vp, POINTER(vp), POINTER(vp), vp, vp, d, vp, sz, vp]),
@@ -79,7 +82,7 @@ def _load():
         "pdmrg_davidson_precond": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
                                        vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d]),
         "pdmrg_davidson_ex": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
-                                  vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d, i, i, POINTER(i)]),
+                                  vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d, i, i, POINTER(i), i]),
         "pdmrg_vec_precond": (i, [i, ll, vp, vp, d, d, d, vp, vp, sz, vp]),
         "pdmrg_heff_diag": (i, [i, i, i, i, i, i, vp, vp, vp, d, i, vp, vp]),
         "pdmrg_host_eig": (i, [i, POINTER(d), POINTER(d), POINTER(d)]),

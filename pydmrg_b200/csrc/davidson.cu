@@ -163,7 +163,7 @@ struct Pinned {
     return p;
   }
 };
-Pinned g_pin;
+thread_local Pinned g_pin;      // one staging buffer per host thread (concurrent solves on different streams)
 
 }  // namespace
 }  // namespace pdmrg
@@ -195,7 +195,7 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
                          double* e_out_host, void* vecs_out, long long vecs_stride,
                          int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
                          const void* diag, double pc_floor, int restart_keep = 0, int tol_relative = 0,
-                         int* n_restarts_out = nullptr) {
+                         int* n_restarts_out = nullptr, int stagnation = 0) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(plan != nullptr, "pdmrg_davidson: null plan");
   PDMRG_REQUIRE(restart_keep >= 0 && restart_keep <= 16, "pdmrg_davidson: restart_keep must be in 0..16");
@@ -257,6 +257,8 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
   bool use_pc = diag != nullptr;
   double pc_best = 1e300;
   int pc_stall = 0;
+  double stag_best = 1e300;
+  int stag_count = 0;
 
   for (cyc = 0; cyc < max_cycle; ++cyc) {
     if (fresh) {
@@ -295,6 +297,16 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
     std::vector<int> order(space);
     for (int i = 0; i < space; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[a].real() < w[b].real(); });   // pick_eigs, diag_tools.py:175-179
+    // Tie-break (the reference sorts by the real part alone): a complex-conjugate pair has EQUAL real parts up to
+    // rounding, so the target would flip between its two members from cycle to cycle and the solve would burn all
+    // max_cycle iterations without converging (seen next to s = 0, where the two leading real eigenvalues of the
+    // truncated generator collide).  Among (numerically) equal real parts the larger imaginary part comes first.
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i + 1 < space; ++i) {
+        const cd a = w[order[i]], b = w[order[i + 1]];
+        const double sc = std::max(1.0, std::max(std::abs(a), std::abs(b)));
+        if (std::abs(a.real() - b.real()) <= 1e-9 * sc && a.imag() < b.imag()) std::swap(order[i], order[i + 1]);
+      }
     nr = std::min(nroots, space);
     for (int k = 0; k < nr; ++k) {
       e[k] = w[order[k]];
@@ -349,6 +361,13 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
       else if (++pc_stall > 2 * ms) use_pc = false;
     }
     if (keep.empty()) { ++cyc; break; }                                     // la_tools.py:539-541
+    if (stagnation > 0) {
+      // opt-in: give up on a local problem whose residual has not been halved within `stagnation` cycles (the reference
+      // would go on to max_cycle = 1000).  Next to s = 0 the truncated generator has a nearly defective leading pair and
+      // single-state solves stall at ||r|| ~ 1e-4 whatever the subspace; the sweep moves on with the best Ritz pair.
+      if (last_res < 0.5 * stag_best) { stag_best = last_res; stag_count = 0; }
+      else if (++stag_count >= stagnation) { ++cyc; break; }
+    }
     if (fixed_cycles > 0 && cyc + 1 >= fixed_cycles) { ++cyc; break; }
     fresh = space + nroots > ms;                                            // la_tools.py:544
     if (fresh && thick) {
@@ -497,7 +516,8 @@ extern "C" int pdmrg_davidson_precond(pdmrg_heff_plan* plan, const void* const* 
 //   restart_keep > 0 : thick restart -- the basis is compressed to the restart_keep lowest Ritz vectors instead of
 //                      being thrown away (XS / AX need max_space + 4*nroots + restart_keep rows);
 //   tol_relative     : res_tol is relative to |theta| (ARPACK's stopping rule, scipy eigs(tol=...), diag_tools.py:225);
-//   diag (optional)  : diagonal preconditioner as in pdmrg_davidson_precond.
+//   diag (optional)  : diagonal preconditioner as in pdmrg_davidson_precond;
+//   stagnation > 0   : stop when the residual has not been halved within that many cycles.
 // With the identity preconditioner the expansion vectors are residuals, i.e. the subspace is the Krylov space of the
 // start vector: restart_keep > 0 then IS thick-restarted Arnoldi (Krylov-Schur), the device-resident counterpart of the
 // reference's ARPACK path (calc_eigs_arnoldi, diag_tools.py:214-241).
@@ -508,10 +528,11 @@ extern "C" int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* Ls, c
                                  void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
                                  double* e_out_host, void* vecs_out, long long vecs_stride,
                                  int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
-                                 const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out) {
+                                 const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out,
+                                 int stagnation) {
   PDMRG_REQUIRE(diag == nullptr || pc_floor > 0.0, "pdmrg_davidson_ex: the preconditioner needs a positive floor");
   return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
                        fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
                        vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor, restart_keep,
-                       tol_relative, n_restarts_out);
+                       tol_relative, n_restarts_out, stagnation);
 }

@@ -23,6 +23,9 @@ struct pdmrg_heff_plan {
   std::vector<MixOpDev> mix;                         // per MPO term
   std::vector<std::vector<int>> need_o, need_j;      // per MPO term: flags
   void* dev_blob = nullptr;
+  bool own_blob = true;                              // false: the caller owns the device blob (pdmrg_heff_plan_upload)
+  std::vector<MixOpHost> pending;                    // host operators waiting for pdmrg_heff_plan_upload
+  size_t blob_bytes = 0;
   double flops_dense = 0, flops_sparse = 0, flops_gemm = 0;
   size_t ws_bytes = 0;
   int k0 = 0, kl = 0;      // ket-index range [k0, k0+kl) of the LEFT bond this plan contracts (kl = Dl: all)
@@ -31,7 +34,8 @@ struct pdmrg_heff_plan {
 namespace {
 
 int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mpo, const int* wL,
-               const int* wR, const void* const* Wc_host, const unsigned char* const* mask, int k0 = 0, int klen = -1) {
+               const int* wR, const void* const* Wc_host, const unsigned char* const* mask, int k0 = 0, int klen = -1,
+               bool defer_upload = false) {
   PDMRG_REQUIRE(dtype == PDMRG_F64 || dtype == PDMRG_C128, "heff plan: bad dtype");
   PDMRG_REQUIRE(P > 0 && Dl > 0 && Dr > 0 && n_mpo > 0, "heff plan: bad extents");
   if (klen < 0) klen = Dl;
@@ -102,6 +106,16 @@ int build_plan(pdmrg_heff_plan** out, int dtype, int P, int Dl, int Dr, int n_mp
     const size_t need = align_up(t_elems * 8 * E, 256) + align_up(u_elems * 8 * E, 256);
     if (need > pl->ws_bytes) pl->ws_bytes = need;
   }
+  pl->blob_bytes = blob_bytes ? blob_bytes : 256;
+  if (defer_upload) {
+    // no device allocation, no copy on the legacy stream, no synchronisation: the caller provides the device blob and
+    // the stream (pdmrg_heff_plan_upload) -- plans are created and dropped once per bond step, and cudaMalloc / cudaFree
+    // would synchronise the whole device under the other scan points running concurrently on their own streams
+    pl->own_blob = false;
+    pl->pending = std::move(hosts);
+    *out = pl;
+    return 0;
+  }
   cudaError_t e = cudaMalloc(&pl->dev_blob, blob_bytes ? blob_bytes : 256);
   if (e != cudaSuccess) { set_error("heff plan: cudaMalloc(%zu) failed: %s", blob_bytes, cudaGetErrorString(e)); delete pl; return 1; }
   size_t off = 0;
@@ -136,9 +150,35 @@ extern "C" int pdmrg_heff_plan_create_ketsplit(pdmrg_heff_plan** plan, int dtype
   return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, block_mask_host, k0, klen);
 }
 
+extern "C" int pdmrg_heff_plan_create_host(pdmrg_heff_plan** plan, int dtype, int P, int Dl, int Dr, int n_mpo,
+                                           const int* wL, const int* wR, const void* const* Wc_host,
+                                           const unsigned char* const* block_mask_host, int k0, int klen) {
+  return build_plan(plan, dtype, P, Dl, Dr, n_mpo, wL, wR, Wc_host, block_mask_host, k0, klen, true);
+}
+
+extern "C" size_t pdmrg_heff_plan_blob_bytes(const pdmrg_heff_plan* plan) { return plan ? plan->blob_bytes : 0; }
+
+extern "C" int pdmrg_heff_plan_upload(pdmrg_heff_plan* pl, void* blob_dev, size_t blob_bytes, void* stream_) {
+  PDMRG_REQUIRE(pl && !pl->own_blob && (int)pl->pending.size() == pl->n_mpo, "pdmrg_heff_plan_upload: plan was not created by pdmrg_heff_plan_create_host (or is already uploaded)");
+  PDMRG_REQUIRE(blob_dev != nullptr && blob_bytes >= pl->blob_bytes, "pdmrg_heff_plan_upload: device blob too small");
+  PDMRG_REQUIRE((reinterpret_cast<uintptr_t>(blob_dev) & 255) == 0, "pdmrg_heff_plan_upload: device blob must be 256-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  size_t off = 0;
+  pl->mix.clear();
+  for (int m = 0; m < pl->n_mpo; ++m) {
+    MixOpDev dev;
+    if (upload_mix_op(pl->pending[m], static_cast<unsigned char*>(blob_dev) + off, &dev, stream)) return 1;
+    pl->mix.push_back(dev);
+    off += align_up(pl->pending[m].device_bytes(), 256);
+  }
+  pl->dev_blob = blob_dev;
+  pl->pending.clear();
+  return 0;
+}
+
 extern "C" void pdmrg_heff_plan_destroy(pdmrg_heff_plan* plan) {
   if (!plan) return;
-  if (plan->dev_blob) cudaFree(plan->dev_blob);
+  if (plan->dev_blob && plan->own_blob) cudaFree(plan->dev_blob);
   delete plan;
 }
 
@@ -195,6 +235,7 @@ namespace {
 int heff_apply_impl(pdmrg_heff_plan* pl, const void* const* Ls, const void* const* Rs, const void* x, void* y,
                     double sign, void* workspace, size_t workspace_bytes, cudaStream_t stream, StageTimer* tm) {
   PDMRG_REQUIRE(pl != nullptr, "pdmrg_heff_apply: null plan");
+  PDMRG_REQUIRE((int)pl->mix.size() == pl->n_mpo, "pdmrg_heff_apply: plan not uploaded (pdmrg_heff_plan_upload)");
   PDMRG_REQUIRE(workspace_bytes >= pl->ws_bytes, "pdmrg_heff_apply: workspace too small");
   const int E = pl->dtype == PDMRG_C128 ? 2 : 1;
   const int P = pl->P, Dl = pl->Dl, Dr = pl->Dr;

@@ -137,20 +137,31 @@ Solver* get_solver() {
       s.p_cublasZtrsm = reinterpret_cast<decltype(&cublasZtrsm_v2)>(dlsym(s.blas_lib, "cublasZtrsm_v2"));
       s.p_cublasDtrsm = reinterpret_cast<decltype(&cublasDtrsm_v2)>(dlsym(s.blas_lib, "cublasDtrsm_v2"));
       if (!s.p_cublasCreate || !s.p_cublasSetStream || !s.p_cublasZtrsm || !s.p_cublasDtrsm) { set_error("cublas symbols missing"); return; }
-      if (s.p_cublasCreate(&s.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return; }
     }
-    if (s.p_cusolverDnCreate(&s.handle) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return; }
-    if (s.p_cusolverDnCreateGesvdjInfo(&s.jinfo) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateGesvdjInfo failed"); return; }
-    s.p_cusolverDnXgesvdjSetTolerance(s.jinfo, 1e-15);
-    s.p_cusolverDnXgesvdjSetMaxSweeps(s.jinfo, 100);
-    s.p_cusolverDnXgesvdjSetSortEig(s.jinfo, 1);
-    if (s.p_cusolverDnCreateSyevjInfo(&s.evj) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateSyevjInfo failed"); return; }
-    s.p_cusolverDnXsyevjSetTolerance(s.evj, 1e-15);
-    s.p_cusolverDnXsyevjSetMaxSweeps(s.evj, 100);
-    s.p_cusolverDnXsyevjSetSortEig(s.evj, 1);
     ok = true;
   });
-  return ok ? &s : nullptr;
+  if (!ok) return nullptr;
+  // Handles (and their stream binding) are per host thread: several scan points may be driven concurrently from
+  // different threads on different streams of one GPU (pydmrg_b200/scan.py workers), and a cuSOLVER / cuBLAS handle
+  // carries its stream.
+  thread_local Solver tl;
+  thread_local int tl_state = 0;          // 0 = not created, 1 = ready, -1 = failed
+  if (tl_state == 0) {
+    tl = s;
+    tl_state = -1;
+    if (tl.p_cublasCreate(&tl.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return nullptr; }
+    if (tl.p_cusolverDnCreate(&tl.handle) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return nullptr; }
+    if (tl.p_cusolverDnCreateGesvdjInfo(&tl.jinfo) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateGesvdjInfo failed"); return nullptr; }
+    tl.p_cusolverDnXgesvdjSetTolerance(tl.jinfo, 1e-15);
+    tl.p_cusolverDnXgesvdjSetMaxSweeps(tl.jinfo, 100);
+    tl.p_cusolverDnXgesvdjSetSortEig(tl.jinfo, 1);
+    if (tl.p_cusolverDnCreateSyevjInfo(&tl.evj) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreateSyevjInfo failed"); return nullptr; }
+    tl.p_cusolverDnXsyevjSetTolerance(tl.evj, 1e-15);
+    tl.p_cusolverDnXsyevjSetMaxSweeps(tl.evj, 100);
+    tl.p_cusolverDnXsyevjSetSortEig(tl.evj, 1);
+    tl_state = 1;
+  }
+  return tl_state == 1 ? &tl : nullptr;
 }
 
 struct SvdLayout {

@@ -30,8 +30,16 @@ from ._lib import check, lib
 
 
 def pick_lowest_real(w, v):
-    """pick_eigs, pydmrg/tools/diag_tools.py:175-179: ascending real part."""
-    idx = np.argsort(np.real(w))
+    """pick_eigs, pydmrg/tools/diag_tools.py:175-179: ascending real part -- with a tie-break the reference lacks: among
+    (numerically) equal real parts, i.e. the two members of a complex-conjugate pair, the larger imaginary part comes
+    first, so the target cannot flip between them from cycle to cycle (csrc/davidson.cu)."""
+    idx = list(np.argsort(np.real(w), kind="stable"))
+    for _ in range(2):
+        for i in range(len(idx) - 1):
+            a, b = w[idx[i]], w[idx[i + 1]]
+            if abs(a.real - b.real) <= 1e-9 * max(1.0, abs(a), abs(b)) and a.imag < b.imag:
+                idx[i], idx[i + 1] = idx[i + 1], idx[i]
+    idx = np.asarray(idx)
     return w[idx], v[:, idx]
 
 
@@ -65,7 +73,8 @@ _WS_CACHE = {}
 
 
 def get_workspace(code, n, rows, nroots, device):
-    key = (code, str(device))
+    import threading
+    key = (code, str(device), threading.get_ident())            # one set of slabs per host thread (scan workers)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.n < n or ws.rows < rows or ws.nroots < nroots:
         _WS_CACHE.pop(key, None)
@@ -97,7 +106,7 @@ def _orthonormalise(ops, src, dst, norm_slot, small):
 
 def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
                     res_tol=None, fixed_cycles=None, stats=None, sign=-1.0, diag=None, precond_floor=0.1,
-                    restart_keep=0, tol_relative=False):
+                    restart_keep=0, tol_relative=False, stagnation=0):
     """The same solver sequenced in C++ (csrc/davidson.cu, ``pdmrg_davidson``): one C-ABI call per
     local eigenproblem, operator = ``sign`` * H_eff of ``plan``."""
     ms = max_space + 3 * nroots
@@ -115,9 +124,9 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
             W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
             e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), D._stream())
     n_rs = ctypes.c_int(0)
-    if restart_keep or tol_relative:
+    if restart_keep or tol_relative or stagnation:
         check(lib.pdmrg_davidson_ex(*args, D._ptr(diag), float(precond_floor), int(restart_keep), int(bool(tol_relative)),
-                                    ctypes.byref(n_rs)), "pdmrg_davidson_ex")
+                                    ctypes.byref(n_rs), int(stagnation)), "pdmrg_davidson_ex")
     elif diag is None:
         check(lib.pdmrg_davidson(*args), "pdmrg_davidson")
     else:
@@ -136,7 +145,7 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
 
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
              res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None, diag=None,
-             precond_floor=0.1, restart_keep=0, tol_relative=False):
+             precond_floor=0.1, restart_keep=0, tol_relative=False, stagnation=0):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
@@ -154,6 +163,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     degenerate partners of the target survive the restart: orders of magnitude fewer mat-vecs when the gap closes (scan
     points next to s = 0).  With the identity preconditioner this is thick-restarted Arnoldi (Krylov-Schur).
     ``tol_relative``: ``res_tol`` is relative to |theta| (ARPACK's stopping rule).
+    ``stagnation`` > 0: stop when the residual has not been halved within that many cycles (the reference goes on to
+    max_cycle; nearly defective local problems next to s = 0 stall at ||r|| ~ 1e-4 whatever the subspace).
     ``consensus``: optional callable applied to the small device arrays right before the host reads them
     (sharded sweeps: a broadcast from rank 0, so that every rank takes the same control decisions and the
     collectives inside ``matvec`` stay matched whatever the last bit of a reduction does).
@@ -165,7 +176,8 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
         native = os.environ.get("PDMRG_PY_DAVIDSON", "0") != "1"
     if native and plan is not None and nroots <= 4 and len(x0) <= nroots and n > nroots:
         return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats,
-                               diag=diag, precond_floor=precond_floor, restart_keep=restart_keep, tol_relative=tol_relative)
+                               diag=diag, precond_floor=precond_floor, restart_keep=restart_keep, tol_relative=tol_relative,
+                               stagnation=stagnation)
     max_space = max_space + 3 * nroots
     rows = max_space + nroots + int(restart_keep)
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
@@ -177,6 +189,7 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     gs_norm = W.norms[-2:-1]
 
     use_pc, pc_best, pc_stall = diag is not None, float("inf"), 0
+    stag_best, stag_count = float("inf"), 0
     n_mv = 0
     space = 0
     fresh = True
@@ -244,12 +257,20 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
             else:
                 pc_stall += 1
                 use_pc = pc_stall <= 2 * max_space
+        if stagnation:
+            res_now = float(np.sqrt(dx2.max()))
+            if res_now < 0.5 * stag_best:
+                stag_best, stag_count = res_now, 0
+            else:
+                stag_count += 1
         trial = []
         for k in range(nr):
             if dx2[k] > thresh2 and px2[k] > lindep:               # la_tools.py:505-537
                 ops.normalize(W.R[k][:n], W.norms[2 * k + 1:2 * k + 2], W.R[k][:n])
                 trial.append(W.R[k][:n])
         if not trial:                                              # la_tools.py:539-541
+            break
+        if stagnation and stag_count >= stagnation:
             break
         if fixed_cycles is not None and cyc + 1 >= fixed_cycles:
             break

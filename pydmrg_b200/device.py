@@ -147,21 +147,18 @@ class HeffPlan:
                 raise ValueError("combined operator shape %s != %s" % (self._wc[k].shape, (wL[k] * P, wR[k] * P)))
         wc_ptrs = (ctypes.c_void_p * n_mpo)(*[w.ctypes.data for w in self._wc])
         self._plan = ctypes.c_void_p(0)
-        if k_range is not None:
-            mptrs = None
-            if block_masks is not None:
-                self._masks = [np.ascontiguousarray(m, dtype=np.uint8) for m in block_masks]
-                mptrs = (ctypes.c_void_p * n_mpo)(*[m.ctypes.data for m in self._masks])
-            check(lib.pdmrg_heff_plan_create_ketsplit(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR, wc_ptrs,
-                                                      mptrs, int(k_range[0]), int(k_range[1])), "pdmrg_heff_plan_create_ketsplit")
-        elif block_masks is None:
-            check(lib.pdmrg_heff_plan_create(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR, wc_ptrs),
-                  "pdmrg_heff_plan_create")
-        else:
+        mptrs = None
+        if block_masks is not None:
             self._masks = [np.ascontiguousarray(m, dtype=np.uint8) for m in block_masks]
             mptrs = (ctypes.c_void_p * n_mpo)(*[m.ctypes.data for m in self._masks])
-            check(lib.pdmrg_heff_plan_create_sharded(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR,
-                                                     wc_ptrs, mptrs), "pdmrg_heff_plan_create_sharded")
+        k0, klen = (0, -1) if k_range is None else (int(k_range[0]), int(k_range[1]))
+        # host tables now, device blob owned by torch, the (tiny) copy ordered on the current stream: no cudaMalloc /
+        # cudaFree / legacy-stream synchronisation per bond step (they would stall concurrent sweeps on other streams)
+        check(lib.pdmrg_heff_plan_create_host(ctypes.byref(self._plan), code, P, Dl, Dr, n_mpo, wL, wR, wc_ptrs, mptrs, k0, klen),
+              "pdmrg_heff_plan_create_host")
+        nb = int(lib.pdmrg_heff_plan_blob_bytes(self._plan))
+        self._blob = torch.empty(nb, dtype=torch.uint8, device=self.Ls[0].device)
+        check(lib.pdmrg_heff_plan_upload(self._plan, _ptr(self._blob), nb, _stream()), "pdmrg_heff_plan_upload")
         self._Lp = (ctypes.c_void_p * n_mpo)(*[t.data_ptr() for t in self.Ls])
         self._Rp = (ctypes.c_void_p * n_mpo)(*[t.data_ptr() for t in self.Rs])
         self.ws_bytes = int(lib.pdmrg_heff_workspace_bytes(self._plan))

@@ -133,7 +133,7 @@ def check_overlap(guess, vecs, E, preserveState, ctx):
 def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, edgePreserveState=True,
               orthonormalize=False, oneSite=True, ctx=None, stats=None, res_tol=None, lindep=1e-14,
               fixed_cycles=None, return_device=None, plan=None, native=None, max_cycle=1000, shard=None, max_space=12,
-              precond=None, precond_floor=0.1, restart_keep=0, arnoldi_tol=1e-5):
+              precond=None, precond_floor=0.1, restart_keep=0, arnoldi_tol=1e-5, stagnation=0):
     """calc_eigs, diag_tools.py:292-313.  Returns (E, vecs, ovlp): E scalar (nStates == 1) or
     array; vecs (n, k) -- NumPy when the MPS was NumPy, CUDA tensor otherwise.
 
@@ -143,7 +143,8 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     cannot drift apart.  ``max_space``: Davidson subspace before a restart (la_tools.py:318 default 12, widened by
     3 per root, :412); a larger one trades vector passes for fewer mat-vecs in cold sweeps.  ``precond='diag'``:
     diagonal Davidson preconditioner built from diag(H_eff) (davidson.davidson) instead of the reference's identity.
-    ``restart_keep`` > 0: thick restart of the Davidson subspace (davidson.davidson).
+    ``restart_keep`` > 0: thick restart of the Davidson subspace; ``stagnation`` > 0: stop a solve whose residual has not
+    been halved within that many cycles (both davidson.davidson; opt-in, beyond the reference's algorithm).
 
     ``alg='arnoldi'`` (calc_eigs_arnoldi, diag_tools.py:214-241: ARPACK ``eigs(k=nStates, which='SR', tol=1e-5, v0=guess)``)
     runs DEVICE-RESIDENT thick-restarted Arnoldi: the same Krylov kernels and C++ loop with the identity preconditioner
@@ -179,14 +180,15 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
         vals, vecs = davidson(lambda x, y: sharded.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=None,
                               native=False, max_cycle=max_cycle, consensus=shard.consensus, max_space=max_space,
-                              restart_keep=restart_keep, **pc)
+                              restart_keep=restart_keep, stagnation=stagnation, **pc)
         E = -vals
         if stats is not None:
             stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
     elif alg == "davidson":
         vals, vecs = davidson(lambda x, y: plan.apply(x, y, -1.0), guesses, n, ctx.code, ctx.device, nroots=nS,
                               lindep=lindep, res_tol=res_tol, fixed_cycles=fixed_cycles, stats=stats, plan=plan,
-                              native=native, max_cycle=max_cycle, max_space=max_space, restart_keep=restart_keep, **pc)
+                              native=native, max_cycle=max_cycle, max_space=max_space, restart_keep=restart_keep,
+                              stagnation=stagnation, **pc)
         E = -vals                                               # diag_tools.py:265,273
     elif alg == "exact":
         E, vecs = _eigs_exact(plan, n, nS, ctx)

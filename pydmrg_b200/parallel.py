@@ -59,6 +59,8 @@ class WorkQueue:
         self.key = "pdmrg_workqueue_%d" % WorkQueue._calls
         self.local = 0
         self.store = None
+        import threading
+        self._lock = threading.Lock()
         if world > 1:
             self.store = store if store is not None else dist.distributed_c10d._get_default_store()
 
@@ -66,11 +68,12 @@ class WorkQueue:
         return self
 
     def __next__(self):
-        if self.store is None:
-            pos = self.local
-            self.local += 1
-        else:
-            pos = int(self.store.add(self.key, 1)) - 1
+        with self._lock:                                         # several worker threads of one rank share the queue
+            if self.store is None:
+                pos = self.local
+                self.local += 1
+            else:
+                pos = int(self.store.add(self.key, 1)) - 1
         if pos >= len(self.order):
             raise StopIteration
         return self.order[pos]

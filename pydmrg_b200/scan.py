@@ -19,7 +19,7 @@ from .parallel import WorkQueue, gather_scan, gather_scan_dynamic, scan_indices
 
 def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
              twoSite=True, dtype="c128", continuation=False, ramp_res_tol=1e-5, stats=None, schedule="static", order=None,
-             **solver):
+             workers=1, seed=None, **solver):
     """Run ``run_dmrg(mpo_of(v), mbd=...)`` for every v in ``values`` (this rank's block only).
 
     Every point cold-starts through the chi ramp by default: the ramp stages run one sweep with a
@@ -38,46 +38,99 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     ``order`` (default: as given; pass the expected-most-expensive first) whenever it is free (parallel.WorkQueue: one
     atomic counter in the process group's store, nothing on the data path).
 
+    ``workers`` > 1 (cold starts; implies the dynamic schedule): that many host threads of this rank each drive their own
+    scan point on their own CUDA stream of the SAME GPU.  Most of a cold point is latency-bound (bond dimensions 2..64
+    in the chi ramp and at the chain ends: a Davidson cycle is ~12 tiny kernels and a host round trip), so one point
+    leaves the GPU idle most of the time; concurrent points fill it.  The C-ABI calls release the GIL, the library keeps
+    its cuSOLVER / cuBLAS handles, pinned staging and stream-K scratch per thread / per stream.
+    ``seed``: the random start of point i is drawn from np.random.seed(seed + i) (reproducible whatever the schedule);
+    default: the global NumPy state as the reference uses it (only reproducible with one worker and a static schedule).
+
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
     rank's points, points: their indices)."""
     from .dmrg import run_dmrg
     n = len(values)
     interleave = not continuation          # cold starts: every world-th point (balanced); continuation: blocks
-    dynamic = schedule == "dynamic" and not continuation
+    workers = max(1, int(workers))
     if schedule not in ("static", "dynamic"):
         raise ValueError("schedule must be 'static' or 'dynamic'")
+    dynamic = (schedule == "dynamic" or workers > 1) and not continuation
     if dynamic:
         todo = WorkQueue(list(range(n)) if order is None else [int(i) for i in order], rank, world, dist)
-        mine = []
     else:
-        todo = mine = scan_indices(n, rank, world, interleave)
-    E_loc, EE_loc, secs = [], [], []
-    prev = None
-    for idx in todo:
-        if dynamic:
-            mine.append(idx)
-        mpo = mpo_of(values[idx])
-        t0 = time.perf_counter()
-        if prev is None or not continuation:
-            # cold start: chi ramp with in-memory continuation between stages
-            guess = None
-            stages = [c for c in ramp if c < mbd] + [mbd]
-            for chi in stages:
-                last = chi == mbd
-                opts = dict(solver)
-                if not last and ramp_res_tol is not None:
-                    opts["res_tol"] = ramp_res_tol
-                out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
-                               initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=stats, **opts)
-                # one-site runs leave the centre at gaugeSiteSave = N//2+1 (dmrg.py:322), two-site ones at site 0
-                guess = out[-1] if twoSite else (_grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd])),
-                                                 len(mpo[0]) // 2 + 1)
-        else:
-            out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,
-                           dtype=dtype, returnState=True, stats=stats, **solver)
-        secs.append(time.perf_counter() - t0)
-        E_loc.append(out[0]); EE_loc.append(out[1])
-        prev = out[-1] if twoSite else (out[-1], len(mpo[0]) // 2 + 1)
+        todo = scan_indices(n, rank, world, interleave)
+    done = []                                                    # (index, E, EE, seconds) of this rank
+    import threading
+    seed_lock = threading.Lock()
+
+    def first_guess(idx, chi):
+        """Random right-canonical start of point idx (dmrg.py:363-366), drawn under a lock from a per-point seed."""
+        if seed is None:
+            return None
+        from . import mps as mps_tools
+        with seed_lock:
+            np.random.seed(int(seed) + int(idx))
+            return mps_tools.make_all_mps_right(mps_tools.create_all_mps(len(mpo_of(values[idx])[0]), chi, 1))
+
+    def solve_points(points, ctx, st):
+        prev = None
+        for idx in points:
+            mpo = mpo_of(values[idx])
+            t0 = time.perf_counter()
+            if prev is None or not continuation:
+                # cold start: chi ramp with in-memory continuation between stages
+                stages = [c for c in ramp if c < mbd] + [mbd]
+                guess = first_guess(idx, stages[0])
+                for chi in stages:
+                    last = chi == mbd
+                    opts = dict(solver)
+                    if not last and ramp_res_tol is not None:
+                        opts["res_tol"] = ramp_res_tol
+                    out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
+                                   initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=st, ctx=ctx, **opts)
+                    # one-site runs leave the centre at gaugeSiteSave = N//2+1 (dmrg.py:322), two-site ones at site 0
+                    guess = out[-1] if twoSite else (_grow(out[-1], min([c for c in list(ramp) + [mbd] if c > chi] or [mbd])),
+                                                     len(mpo[0]) // 2 + 1)
+            else:
+                out = run_dmrg(mpo, mbd=mbd, tol=tol, maxIter=maxIter, minIter=minIter, initGuess=prev, twoSite=twoSite,
+                               dtype=dtype, returnState=True, stats=st, ctx=ctx, **solver)
+            done.append((idx, out[0], out[1], time.perf_counter() - t0))
+            prev = out[-1] if twoSite else (out[-1], len(mpo[0]) // 2 + 1)
+
+    if workers == 1:
+        solve_points(todo, None, stats)
+    else:
+        import torch
+        from .core import Context
+        dev_index = torch.cuda.current_device()
+        errors, all_stats = [], []
+
+        def worker():
+            try:
+                torch.cuda.set_device(dev_index)
+                with torch.cuda.stream(torch.cuda.Stream(device=dev_index)):
+                    st = {} if stats is not None else None
+                    all_stats.append(st)
+                    solve_points(todo, Context(dtype), st)
+                    torch.cuda.current_stream().synchronize()
+            except BaseException as exc:                         # surface the first failure in the caller
+                errors.append(exc)
+
+        threads = [threading.Thread(target=worker, name="pdmrg-scan-%d" % k) for k in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        if stats is not None:
+            for st in all_stats:
+                for key, val in (st or {}).items():
+                    if isinstance(val, (int, float)) and key != "last_residual":
+                        stats[key] = stats.get(key, 0) + val
+    done.sort(key=lambda r: r[0])
+    mine = [r[0] for r in done]
+    E_loc, EE_loc, secs = [r[1] for r in done], [r[2] for r in done], [r[3] for r in done]
     if dynamic:
         return {"E": gather_scan_dynamic(mine, E_loc, n, world, dist), "EE": gather_scan_dynamic(mine, EE_loc, n, world, dist),
                 "sec": secs, "points": mine}
@@ -105,6 +158,10 @@ def main():
                     help="give every local rank its own slice of the host cores (the scan is host-latency bound)")
     ap.add_argument("--precond", default=None, choices=[None, "diag"], help="Davidson preconditioner (default: the reference's identity)")
     ap.add_argument("--max-space", type=int, default=12, help="Davidson subspace before a restart (reference: 12)")
+    ap.add_argument("--workers", type=int, default=3, help="concurrent scan points per GPU (host threads, one CUDA stream each)")
+    ap.add_argument("--restart-keep", type=int, default=0, help="thick restart of the Davidson subspace (0: the reference's restart)")
+    ap.add_argument("--stagnation", type=int, default=30, help="stop a local solve whose residual was not halved within this many cycles "
+                                                               "(0: the reference's behaviour, up to 1000 cycles per solve)")
     ap.add_argument("--schedule", default="dynamic", choices=["static", "dynamic"],
                     help="dynamic: a rank takes the next point when it is free, points nearest s = 0 (the expensive ones) first")
     args = ap.parse_args()
@@ -140,7 +197,8 @@ def main():
     stats = {}
     order = [int(i) for i in np.argsort(np.abs(s_vals), kind="stable")]        # the gap closes at s = 0: those points first
     res = run_scan(mpo_of, s_vals, args.chi, rank, world, dist if world > 1 else None, maxIter=args.max_iter, stats=stats,
-                   precond=args.precond, max_space=args.max_space, schedule=args.schedule, order=order)
+                   precond=args.precond, max_space=args.max_space, schedule=args.schedule, order=order, workers=args.workers,
+                   seed=0, restart_keep=args.restart_keep, stagnation=args.stagnation)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     per_rank = [{"rank": rank, "sec": round(sum(res["sec"]), 3), "points": len(res["points"]), "cycles": stats.get("cycles"),
                  "n_matvec": stats.get("n_matvec")}]
@@ -155,7 +213,8 @@ def main():
         print(json.dumps({"metric": "s_points_per_hour", "value": args.points / dt * 3600.0, "n_gpus": world,
                           "host_cores": os.cpu_count(), "cores_per_rank": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
                           "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt, "per_rank": per_rank,
-                          "precond": args.precond, "max_space": args.max_space, "schedule": args.schedule, "blas_threads_per_rank": blas_threads,
+                          "precond": args.precond, "max_space": args.max_space, "schedule": args.schedule, "workers": args.workers,
+                          "restart_keep": args.restart_keep, "stagnation": args.stagnation, "blas_threads_per_rank": blas_threads,
                           "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
     if world > 1:
         dist.destroy_process_group()

@@ -190,3 +190,114 @@ def test_config3_scan_points_vs_oracle(P):
         Eo, EEo = orc.run_dmrg_twosite(mpo_of(s), chi, n_sweeps=5)[:2]
         assert abs(res["E"][i] - Eo) < 1e-7 * max(1.0, abs(Eo)), (s, res["E"][i], Eo)
         assert abs(res["EE"][i] - EEo) < 1e-6, (s, res["EE"][i], EEo)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scans across the s = 0 transition against dense ED; concurrent workers; thick restart; device Arnoldi
+# ---------------------------------------------------------------------------------------------------------------
+def dense_from_mpo(mpo):
+    """2^N x 2^N matrix of an MPO list (sum over its terms; None = identity), physical index of site 0 slowest."""
+    N = len(mpo[0])
+    tot = 0
+    for op in mpo:
+        cur = np.ones((1, 1, 1), dtype=np.complex128)
+        for site in range(N):
+            W = op[site]
+            if W is None:
+                W = np.einsum("ab,ij->abij", np.eye(cur.shape[0]), np.eye(2))
+            cur = np.einsum("aij,abkl->bikjl", cur, W).reshape(W.shape[1], cur.shape[1] * 2, cur.shape[2] * 2)
+        tot = tot + cur[0]
+    return tot
+
+
+S_ACROSS = [-0.12, -0.06, -0.02, 0.01, 0.03, 0.08, 0.15]
+
+
+@pytest.fixture(scope="module")
+def ed_across():
+    from pydmrg_b200 import mpo as M
+    out = []
+    for s in S_ACROSS:
+        w = np.linalg.eigvals(dense_from_mpo(M.asep_mpo(10, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, s))))
+        w = w[np.argsort(-w.real)]
+        out.append((w[0].real, w[1].real))
+    return out
+
+
+def test_scan_across_the_transition_vs_ed(P, ed_across):
+    """configs[3] in miniature against dense ED (N=10, chi=32 = exact): seven s values across s=0, where the two leading
+    eigenvalues of the tilted generator approach each other.  (1) cold starts, dynamic schedule, 2 concurrent workers
+    (threads + streams on one GPU), thick restart; (2) the same with one worker and the reference's restart -- E to 1e-9."""
+    mpo_of = lambda s: P.mpo.asep_mpo(10, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    for opts in (dict(workers=2, restart_keep=4), dict(workers=1)):
+        st = {}
+        res = P.scan.run_scan(mpo_of, S_ACROSS, 32, ramp=(8,), maxIter=6, tol=1e-12, res_tol=1e-11, schedule="dynamic", seed=11,
+                              stats=st, **opts)
+        assert sorted(res["points"]) == list(range(len(S_ACROSS)))
+        for i, s in enumerate(S_ACROSS):
+            assert abs(res["E"][i] - ed_across[i][0]) < 1e-9 * max(1.0, abs(ed_across[i][0])), (opts, s, res["E"][i], ed_across[i])
+        if opts.get("restart_keep"):
+            assert st.get("n_thick_restarts", 0) > 0
+
+
+def test_continuation_scan_two_states_vs_ed(P, ed_across):
+    """The reference's scan mode (scripts/asep/current/bondDimConv.py:19-27): serial continuation, every point
+    warm-started from the previous point's states, nStates=2 so that both branches of the transition stay in the
+    targeted space -- E and the gap E0 - E1 against dense ED at every s (one-site sweeps, the reference's algorithm;
+    chi = 32 is exact at N=10)."""
+    mpo_of = lambda s: P.mpo.asep_mpo(10, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, float(s)))
+    np.random.seed(5)
+    prev, Es, gaps = None, [], []
+    for s in S_ACROSS:
+        out = P.dmrg.run_dmrg(mpo_of(s), mbd=32, tol=1e-11, maxIter=8, nStates=2, initGuess=prev, returnState=True, res_tol=1e-11)
+        Es.append(out[0]); gaps.append(out[2])
+        prev = (out[-1], 10 // 2 + 1)
+    for i, s in enumerate(S_ACROSS):
+        e0, e1 = ed_across[i]
+        assert abs(Es[i] - e0) < 1e-8 * max(1.0, abs(e0)), (s, Es[i], e0)
+        assert abs(gaps[i] - (e0 - e1)) < 1e-6 * max(1.0, abs(e0)), (s, gaps[i], e0 - e1)
+    res = P.scan.run_scan(mpo_of, S_ACROSS, 32, ramp=(), maxIter=8, tol=1e-11, res_tol=1e-11, continuation=True, twoSite=False,
+                          nStates=2)
+    for i, s in enumerate(S_ACROSS):
+        assert abs(res["E"][i] - ed_across[i][0]) < 1e-8 * max(1.0, abs(ed_across[i][0])), (s, res["E"][i], ed_across[i])
+
+
+@pytest.mark.parametrize("dtype", ["c128", "f64"])
+def test_thick_restart_and_device_arnoldi_on_a_local_problem(P, dtype):
+    """A physical two-site local problem with a nearly degenerate leading pair (ASEP next to s=0) / the Heisenberg chain:
+    the reference's restart, thick restarts (C++ loop and Python loop) and device-resident thick-restarted Arnoldi
+    (alg='arnoldi') against dense diagonalisation of the same operator (alg='exact')."""
+    from oracle import dmrg_oracle as orc
+    from pydmrg_b200 import davidson as dav, eigs
+    N, chi = 12, 16
+    mpo = P.mpo.heisenberg_mpo(N) if dtype == "f64" else P.mpo.asep_mpo(N, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, 0.01))
+    c = P.core.Context(dtype)
+    np.random.seed(5)
+    mps = orc.make_mps_right(orc.random_mps(N, chi))
+    env = orc.build_env(mps, mpo, chi, gauge_site=0, mode="blas")
+    site = N // 2 - 1
+    M = [[c.dev(np.real(t) if dtype == "f64" else t) for t in mps]]
+    F = [[c.dev(np.real(t) if dtype == "f64" else t) for t in Fm] for Fm in env]
+    Eex, _, _ = eigs.calc_eigs(M, mpo, F, site, 1, alg="exact", oneSite=False, ctx=c)
+    res = {}
+    for tag, kw in (("reference", {}), ("thick", {"restart_keep": 4}), ("thick_py", {"restart_keep": 4, "native": False}),
+                    ("thick_wide", {"restart_keep": 6, "max_space": 24})):
+        st = {}
+        E, v, _ = eigs.calc_eigs(M, mpo, F, site, 1, alg="davidson", oneSite=False, ctx=c, stats=st, res_tol=1e-10, **kw)
+        res[tag] = (E, st["n_matvec"], st.get("n_thick_restarts", 0))
+        assert abs(E - Eex) < 1e-9 * max(1.0, abs(Eex)), (tag, E, Eex)
+    if res["reference"][1] > 40:                                 # the problem needed restarts at all
+        assert res["thick"][2] > 0 and res["thick_py"][2] > 0
+        assert res["thick"][1] <= res["reference"][1] + 2, res
+    st = {}
+    Ea, va, _ = eigs.calc_eigs(M, mpo, F, site, 1, alg="arnoldi", oneSite=False, ctx=c, stats=st)
+    assert abs(Ea - Eex) < 1e-5 * max(1.0, abs(Eex)), (Ea, Eex)                       # ARPACK's tol = 1e-5 (diag_tools.py:225)
+    Eh, _, _ = eigs.calc_eigs(M, mpo, F, site, 1, alg="arnoldi_host", oneSite=False, ctx=c)
+    assert abs(Ea - Eh) < 1e-5 * max(1.0, abs(Eex))
+    torch.manual_seed(3)
+    M2 = M + [[t + 0.3 * torch.randn_like(t) for t in M[0]]]                          # a second, different guess state
+    E2, _, _ = eigs.calc_eigs(M2, mpo, F, site, 2, alg="arnoldi", oneSite=False, ctx=c)
+    E2x, _, _ = eigs.calc_eigs(M2, mpo, F, site, 2, alg="exact", oneSite=False, ctx=c)
+    # the second state may be one member of a complex-conjugate pair (either member is a valid answer): compare Re and |Im|
+    fold = lambda e: np.asarray([complex(z.real, abs(z.imag)) for z in np.asarray(e)])
+    assert np.max(np.abs(fold(E2) - fold(E2x))) < 1e-4 * max(1.0, abs(Eex)), (E2, E2x)
