@@ -129,6 +129,9 @@ int pdmrg_ipc_free(void* dev_ptr);
 int pdmrg_comm_create(pdmrg_comm** comm, int rank, int world, void* const* Zpeer, void* const* Ypeer,
                       void* const* Fpeer);
 void pdmrg_comm_destroy(pdmrg_comm* comm);
+/* Sticky error word of this rank's flag buffer (the flag buffer needs (2*world + 1) * 8 bytes): non-zero when a flag wait
+ * gave up after several seconds (a peer died or diverged).  Synchronises the stream. */
+int pdmrg_comm_error(pdmrg_comm* comm, unsigned long long* err_out, void* stream);
 size_t pdmrg_comm_z_bytes(const pdmrg_heff_plan* plan, int world);
 size_t pdmrg_comm_y_bytes(const pdmrg_heff_plan* plan);
 int pdmrg_heff_needed_j(const pdmrg_heff_plan* plan, int mpo, unsigned int* mask_out);
@@ -278,6 +281,18 @@ int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* L_host_ptrs, con
                       int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
                       const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out,
                       int stagnation);
+/* pdmrg_davidson_ex over a SHARDED operator: `plan` = this rank's ket-split shard, every mat-vec =
+ * pdmrg_heff_apply_fused_ket through `comm`.  Identical start vectors and options on every rank; the ranks then run in
+ * lock step without exchanging control scalars (bit-identical images, fixed-order reductions). */
+int pdmrg_davidson_sharded(pdmrg_heff_plan* plan, pdmrg_comm* comm, const void* const* L_host_ptrs, const void* const* R_host_ptrs,
+                           double sign, int dtype, long long n, const void* x0, long long x0_stride, int nx0, int nroots,
+                           int max_space, double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                           void* XS, void* AX, void* Rv, long long stride,
+                           void* heff_workspace, size_t heff_workspace_bytes, void* scratch, size_t scratch_bytes,
+                           double* e_out_host, void* vecs_out, long long vecs_stride,
+                           int* n_matvec_out, int* cycles_out, double* last_residual_out, void* stream,
+                           const void* diag, double pc_floor, int restart_keep, int tol_relative, int* n_restarts_out,
+                           int stagnation);
 /* r <- r / (diag - theta) element-wise with the floor above; norm2_dev[0] = ||r||^2 of the result.  scratch as for the
  * other vector kernels (pdmrg_vec_scratch_bytes). */
 int pdmrg_vec_precond(int dtype, long long n, void* r, const void* diag, double theta_re, double theta_im,

@@ -56,6 +56,7 @@ def _load():
         "pdmrg_ipc_free": (i, [vp]),
         "pdmrg_comm_create": (i, [POINTER(vp), i, i, POINTER(vp), POINTER(vp), POINTER(vp)]),
         "pdmrg_comm_destroy": (None, [vp]),
+        "pdmrg_comm_error": (i, [vp, POINTER(ctypes.c_ulonglong), vp]),
         "pdmrg_comm_z_bytes": (sz, [vp, i]),
         "pdmrg_comm_y_bytes": (sz, [vp]),
         "pdmrg_heff_needed_j": (i, [vp, i, POINTER(ctypes.c_uint)]),
@@ -83,6 +84,8 @@ def _load():
                                        vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d]),
         "pdmrg_davidson_ex": (i, [vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
                                   vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d, i, i, POINTER(i), i]),
+        "pdmrg_davidson_sharded": (i, [vp, vp, POINTER(vp), POINTER(vp), d, i, ll, vp, ll, i, i, i, d, d, i, i, vp, vp, vp, ll, vp, sz,
+                                       vp, sz, POINTER(d), vp, ll, POINTER(i), POINTER(i), POINTER(d), vp, vp, d, i, i, POINTER(i), i]),
         "pdmrg_vec_precond": (i, [i, ll, vp, vp, d, d, d, vp, vp, sz, vp]),
         "pdmrg_heff_diag": (i, [i, i, i, i, i, i, vp, vp, vp, d, i, vp, vp]),
         "pdmrg_host_eig": (i, [i, POINTER(d), POINTER(d), POINTER(d)]),

@@ -195,7 +195,7 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
                          double* e_out_host, void* vecs_out, long long vecs_stride,
                          int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
                          const void* diag, double pc_floor, int restart_keep = 0, int tol_relative = 0,
-                         int* n_restarts_out = nullptr, int stagnation = 0) {
+                         int* n_restarts_out = nullptr, int stagnation = 0, pdmrg_comm* comm = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PDMRG_REQUIRE(plan != nullptr, "pdmrg_davidson: null plan");
   PDMRG_REQUIRE(restart_keep >= 0 && restart_keep <= 16, "pdmrg_davidson: restart_keep must be in 0..16");
@@ -275,7 +275,11 @@ static int davidson_impl(pdmrg_heff_plan* plan, const void* const* Ls, const voi
     const int rnow = (int)trial.size(), head = space;
     for (int k = 0; k < rnow; ++k) {
       if (trial[k] != xs(head + k)) PDMRG_CHECK_CUDA(cudaMemcpyAsync(xs(head + k), trial[k], (size_t)n * eb, cudaMemcpyDeviceToDevice, stream));
-      if (pdmrg_heff_apply(plan, Ls, Rs, xs(head + k), ax(head + k), sign, heff_ws, heff_ws_bytes, stream)) return 1;
+      // comm != NULL: the plan is this rank's ket-split shard and the exchange is fused into the kernels (heff.cu
+      // pdmrg_heff_apply_fused_ket): every rank gets a bit-identical image, so all ranks run this loop in lock step
+      if (comm ? pdmrg_heff_apply_fused_ket(plan, comm, Ls, Rs, xs(head + k), ax(head + k), sign, heff_ws, heff_ws_bytes, stream)
+               : pdmrg_heff_apply(plan, Ls, Rs, xs(head + k), ax(head + k), sign, heff_ws, heff_ws_bytes, stream))
+        return 1;
       ++n_mv;
     }
     space = head + rnow;
@@ -535,4 +539,27 @@ extern "C" int pdmrg_davidson_ex(pdmrg_heff_plan* plan, const void* const* Ls, c
                        fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
                        vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor, restart_keep,
                        tol_relative, n_restarts_out, stagnation);
+}
+
+// The loop of pdmrg_davidson_ex over a SHARDED operator: `plan` is this rank's ket-split shard
+// (pdmrg_heff_plan_create_ketsplit / _create_host with a ket range), `comm` the peer-memory communicator; each mat-vec is
+// pdmrg_heff_apply_fused_ket.  Every rank must call it with identical start vectors and options: the images are
+// bit-identical on all ranks and every vector kernel reduces in a fixed order, so the ranks take identical control
+// decisions without exchanging a single control scalar (a rank that diverged would trip the bounded flag waits:
+// pdmrg_comm_error).
+extern "C" int pdmrg_davidson_sharded(pdmrg_heff_plan* plan, pdmrg_comm* comm, const void* const* Ls, const void* const* Rs,
+                                      double sign, int dtype, long long n, const void* x0, long long x0_stride, int nx0,
+                                      int nroots, int max_space, double lindep, double res_tol, int max_cycle, int fixed_cycles,
+                                      void* XS_, void* AX_, void* Rv_, long long stride,
+                                      void* heff_ws, size_t heff_ws_bytes, void* scratch, size_t scratch_bytes,
+                                      double* e_out_host, void* vecs_out, long long vecs_stride,
+                                      int* n_matvec_out, int* cycles_out, double* last_res_out, void* stream_,
+                                      const void* diag, double pc_floor, int restart_keep, int tol_relative,
+                                      int* n_restarts_out, int stagnation) {
+  PDMRG_REQUIRE(comm != nullptr, "pdmrg_davidson_sharded: null communicator");
+  PDMRG_REQUIRE(diag == nullptr || pc_floor > 0.0, "pdmrg_davidson_sharded: the preconditioner needs a positive floor");
+  return davidson_impl(plan, Ls, Rs, sign, dtype, n, x0, x0_stride, nx0, nroots, max_space, lindep, res_tol, max_cycle,
+                       fixed_cycles, XS_, AX_, Rv_, stride, heff_ws, heff_ws_bytes, scratch, scratch_bytes, e_out_host,
+                       vecs_out, vecs_stride, n_matvec_out, cycles_out, last_res_out, stream_, diag, pc_floor, restart_keep,
+                       tol_relative, n_restarts_out, stagnation, comm);
 }

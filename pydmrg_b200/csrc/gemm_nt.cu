@@ -630,7 +630,7 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
     int bm = choose_bm(M, p.tiles_n, nbatch);
     // stream-K when whole tiles quantise badly over the SMs (bond dimensions <= 512: a fraction of a wave to a few
     // waves): cost in k-iterations of the busiest SM, data-parallel = ceil(tiles / SMs) * ktot (x 0.52 for the 64-row
-    // tile), stream-K = ceil(tiles * ktot / SMs) + ~3 for the partial store / fix-up
+    // tile), stream-K = ceil(tiles * ktot / SMs) + ~4 for the partial store / fix-up (measured: ~10 us)
     p.streamk = 0; p.sk_per = 0; p.sk_partial = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
     int grid_sk = 0;
     {
@@ -639,9 +639,9 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
       const long long t128 = ((M + 127) / 128) * (long long)p.tiles_n * nbatch, t64 = ((M + 63) / 64) * (long long)p.tiles_n * nbatch;
       const double dp = bm == 128 ? (double)((t128 + sms - 1) / sms) * ktot : (double)((t64 + sms - 1) / sms) * ktot * 0.52;
       const long long iters = t128 * ktot;
-      const double sk = (double)((iters + sms - 1) / sms) + 3.0;
+      const double sk = (double)((iters + sms - 1) / sms) + 4.0;
       const int mode = g_streamk_mode.load();
-      if (!scatter && mode != 0 && iters >= 8 && ktot >= 2 && (mode == 2 || (sk < 0.9 * dp && t128 < 6 * sms))) {
+      if (!scatter && mode != 0 && iters >= 8 && ktot >= 2 && (mode == 2 || (sk < 0.95 * dp && t128 < 6 * sms))) {
         long long g = sms < iters / 4 ? sms : iters / 4;
         if (g < 1) g = 1;
         const long long per = (iters + g - 1) / g;

@@ -106,9 +106,10 @@ def _orthonormalise(ops, src, dst, norm_slot, small):
 
 def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
                     res_tol=None, fixed_cycles=None, stats=None, sign=-1.0, diag=None, precond_floor=0.1,
-                    restart_keep=0, tol_relative=False, stagnation=0):
+                    restart_keep=0, tol_relative=False, stagnation=0, comm=None):
     """The same solver sequenced in C++ (csrc/davidson.cu, ``pdmrg_davidson``): one C-ABI call per
-    local eigenproblem, operator = ``sign`` * H_eff of ``plan``."""
+    local eigenproblem, operator = ``sign`` * H_eff of ``plan``.  ``comm`` (a pdmrg_comm handle): ``plan`` is this rank's
+    ket-split shard and every mat-vec is the fused peer-memory exchange (``pdmrg_davidson_sharded``)."""
     ms = max_space + 3 * nroots
     rows = ms + nroots + int(restart_keep)
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)
@@ -124,7 +125,10 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
             W.XS.stride(0), D._ptr(ws), ws.numel(), D._ptr(W.native_scratch), W.native_scratch.numel(),
             e_host, D._ptr(out), out.stride(0), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), D._stream())
     n_rs = ctypes.c_int(0)
-    if restart_keep or tol_relative or stagnation:
+    if comm is not None:
+        check(lib.pdmrg_davidson_sharded(args[0], comm, *args[1:], D._ptr(diag), float(precond_floor), int(restart_keep),
+                                         int(bool(tol_relative)), ctypes.byref(n_rs), int(stagnation)), "pdmrg_davidson_sharded")
+    elif restart_keep or tol_relative or stagnation:
         check(lib.pdmrg_davidson_ex(*args, D._ptr(diag), float(precond_floor), int(restart_keep), int(bool(tol_relative)),
                                     ctypes.byref(n_rs), int(stagnation)), "pdmrg_davidson_ex")
     elif diag is None:
@@ -145,7 +149,7 @@ def davidson_native(plan, x0, n, code, device, nroots=1, max_space=12, lindep=1e
 
 def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, max_cycle=1000,
              res_tol=None, fixed_cycles=None, stats=None, plan=None, native=None, consensus=None, diag=None,
-             precond_floor=0.1, restart_keep=0, tol_relative=False, stagnation=0):
+             precond_floor=0.1, restart_keep=0, tol_relative=False, stagnation=0, comm=None):
     """Eigenpairs with the smallest real part of the operator behind ``matvec(x, y)``
     (y <- A x, both device vectors of length n).
 
@@ -177,7 +181,9 @@ def davidson(matvec, x0, n, code, device, nroots=1, max_space=12, lindep=1e-14, 
     if native and plan is not None and nroots <= 4 and len(x0) <= nroots and n > nroots:
         return davidson_native(plan, x0, n, code, device, nroots, max_space, lindep, max_cycle, res_tol, fixed_cycles, stats,
                                diag=diag, precond_floor=precond_floor, restart_keep=restart_keep, tol_relative=tol_relative,
-                               stagnation=stagnation)
+                               stagnation=stagnation, comm=comm)
+    if comm is not None:
+        raise ValueError("the fused sharded mat-vec is driven by the C++ loop only (nroots <= 4, native=True)")
     max_space = max_space + 3 * nroots
     rows = max_space + nroots + int(restart_keep)
     W = get_workspace(code, n, rows, max(nroots, len(x0)), device)

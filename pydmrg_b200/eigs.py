@@ -171,7 +171,25 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
     if precond not in (None, "diag"):
         raise ValueError("precond must be None or 'diag'")
     pc = dict(diag=plan.diag(-1.0), precond_floor=precond_floor) if (precond == "diag" and alg == "davidson") else {}
-    if alg == "davidson" and sharded is not None:
+    fused = None
+    if alg == "davidson" and sharded is not None and nS <= 4:
+        fused = shard.fused_heff(ctx, mpsL[0], W, F, site, oneSite)
+    if fused is not None:
+        # C++ loop on every rank over the fused peer-memory mat-vec: identical start vectors + bit-identical images +
+        # fixed-order reductions = identical control flow on all ranks, with no collective inside the solve
+        for gk in guesses:
+            shard.consensus(gk)
+        pcf = dict(diag=fused.plan.diag(-1.0), precond_floor=precond_floor) if precond == "diag" else {}
+        vals, vecs = davidson(None, guesses, n, ctx.code, ctx.device, nroots=nS, lindep=lindep, res_tol=res_tol,
+                              fixed_cycles=fixed_cycles, stats=stats, plan=fused.plan, native=True, max_cycle=max_cycle,
+                              max_space=max_space, restart_keep=restart_keep, stagnation=stagnation, comm=fused._comm, **pcf)
+        fused.peer.check()
+        E = -vals
+        fused.close()
+        if stats is not None:
+            stats["n_sharded_solves"] = stats.get("n_sharded_solves", 0) + 1
+            stats["n_fused_sharded_solves"] = stats.get("n_fused_sharded_solves", 0) + 1
+    elif alg == "davidson" and sharded is not None:
         # identical start vectors on every rank: together with the all-reduced images and the deterministic vector
         # kernels this keeps the ranks' Krylov bases identical (a residual of norm 1e-9 that differed by 1e-13
         # between ranks would otherwise become a 1e-4 relative inconsistency of the next, normalised, direction)

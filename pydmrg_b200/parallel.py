@@ -327,10 +327,31 @@ class ShardSpec:
     the MPO bond) -- one NCCL all-reduce of y per mat-vec; with ``shard_env`` the block updates of those bonds
     are split over the ket index of the new block (one all-reduce of the block).  The truncation stays replicated."""
 
-    def __init__(self, rank, world, dist, mode="ket", min_dim=256, shard_env=True):
+    def __init__(self, rank, world, dist, mode="ket", min_dim=256, shard_env=True, fused=True):
         self.rank, self.world, self.dist, self.mode = int(rank), int(world), dist, mode
         self.min_dim = max(int(min_dim), 16 * self.world)       # every rank must own a TMA-aligned ket range
         self.shard_env = bool(shard_env)
+        # fused (ket mode, one MPO term): the local solve runs in the C++ Davidson loop on every rank, each mat-vec with
+        # the exchange fused into the kernels over peer memory (pdmrg_davidson_sharded) -- no NCCL call and no control
+        # broadcast inside a solve; otherwise the Python loop with one NCCL all-reduce per mat-vec
+        self.fused = bool(fused) and mode == "ket"
+        self._peer = None
+
+    def fused_heff(self, ctx, M, W, F, site, oneSite):
+        """This rank's ket-split shard of the local operator bound to the sweep's cached peer communicator, or None when
+        the fused path does not apply (several MPO terms)."""
+        from .eigs import _site_ops
+        if not getattr(self, "fused", False) or len(W) != 1:
+            return None
+        ops, P, shape = _site_ops(M, W, F, site, oneSite, ctx)
+        fz = FusedShardedHeff(ctx.code, P, shape[-2], shape[-1], ops, ctx.ws, self.rank, self.world, self.dist, mode="ket",
+                              comm=self._peer)
+        if fz._own_comm:                                         # first large bond, or a larger one: keep the new buffers
+            if self._peer is not None:
+                self._peer.close()
+            self._peer = fz.peer
+            fz._own_comm = False
+        return fz
 
     def heff(self, ctx, M, W, F, site, oneSite):
         from .eigs import _site_ops
@@ -370,16 +391,91 @@ class ShardSpec:
         return t
 
 
+class PeerComm:
+    """Peer-memory communicator of the fused sharded mat-vec (csrc/comm.cu): three buffers per rank -- the slab buffer Z the
+    peers' GEMM epilogues store into, the staging buffer of the reduced y, the flags -- exchanged ONCE through CUDA IPC.
+    Sized in bytes, so one communicator serves every bond of a sweep whose buffers fit (parallel.ShardSpec caches it)."""
+
+    def __init__(self, z_bytes, y_bytes, rank, world, dist=None):
+        import ctypes
+        import torch
+        from ._lib import check, lib
+        self.rank, self.world = rank, world
+        self.z_bytes, self.y_bytes = int(z_bytes), int(y_bytes)
+        self._lib = lib
+        sizes = [self.z_bytes, self.y_bytes, (2 * world + 1) * 8 + 256]
+        self._own, handles = [], []
+        for nb in sizes:
+            ptr = ctypes.c_void_p(0)
+            hbuf = ctypes.create_string_buffer(64)
+            check(lib.pdmrg_ipc_alloc(nb, ctypes.byref(ptr), hbuf), "pdmrg_ipc_alloc")
+            self._own.append(ptr)
+            handles.append(hbuf.raw)
+        if world > 1:
+            everyone = [None] * world
+            dist.all_gather_object(everyone, handles)
+        else:
+            everyone = [handles]
+        self._opened = []
+        tables = []
+        for k in range(3):
+            arr = (ctypes.c_void_p * world)()
+            for q in range(world):
+                if q == rank:
+                    arr[q] = self._own[k].value
+                else:
+                    ptr = ctypes.c_void_p(0)
+                    check(lib.pdmrg_ipc_open(everyone[q][k], ctypes.byref(ptr)), "pdmrg_ipc_open")
+                    self._opened.append(ptr)
+                    arr[q] = ptr.value
+            tables.append(arr)
+        self.handle = ctypes.c_void_p(0)
+        check(lib.pdmrg_comm_create(ctypes.byref(self.handle), rank, world, tables[0], tables[1], tables[2]), "pdmrg_comm_create")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def fits(self, z_bytes, y_bytes):
+        return self.handle is not None and z_bytes <= self.z_bytes and y_bytes <= self.y_bytes
+
+    def check(self):
+        """Raise if a flag wait of this rank timed out (a peer died or diverged)."""
+        import ctypes
+        from . import device as D
+        from ._lib import check
+        err = ctypes.c_ulonglong(0)
+        check(self._lib.pdmrg_comm_error(self.handle, ctypes.byref(err), D._stream()), "pdmrg_comm_error")
+        if err.value:
+            raise RuntimeError("sharded mat-vec: a peer did not signal epoch %d within the time-out (rank %d)" % (err.value, self.rank))
+
+    def close(self):
+        import torch
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize()
+            self._lib.pdmrg_comm_destroy(self.handle)
+            self.handle = None
+            for p in self._opened:
+                self._lib.pdmrg_ipc_close(p)
+            for p in self._own:
+                self._lib.pdmrg_ipc_free(p)
+            self._opened, self._own = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FusedShardedHeff:
     """MPO-bond-sharded mat-vec whose exchange is done by the kernels themselves over peer memory
     (CUDA IPC + NVLink loads/stores): stage-C GEMM with a scatter epilogue -> flag -> reduce + all-gather
     by peer stores -> flag -> copy.  No NCCL on the data path; ``dist`` is only used once, to ship the
     64-byte IPC handles and the slab masks between the ranks.  world == 1 runs the same kernels on
-    the local buffers."""
+    the local buffers.  ``comm``: an existing PeerComm with large enough buffers (ket mode)."""
 
-    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist=None, mode="bond"):
+    def __init__(self, code, P, Dl, Dr, ops, workspace, rank, world, dist=None, mode="bond", comm=None):
         import ctypes
-        import torch
         from . import device as D
         from ._lib import check, lib
         assert len(ops) == 1, "one MPO term per fused plan"
@@ -396,42 +492,18 @@ class FusedShardedHeff:
             self.plan = D.HeffPlan(code, P, Dl, Dr, ops, workspace, k_range=ket_chunks(Dl, world)[rank])
         self.n = self.plan.n
         self._lib, self._check, self._ct = lib, check, ctypes
-        sizes = [int(lib.pdmrg_comm_z_bytes(self.plan._plan, world)), int(lib.pdmrg_comm_y_bytes(self.plan._plan)),
-                 2 * world * 8 + 256]
-        self._own, handles = [], []
-        for nb in sizes:
-            ptr = ctypes.c_void_p(0)
-            hbuf = ctypes.create_string_buffer(64)
-            check(lib.pdmrg_ipc_alloc(nb, ctypes.byref(ptr), hbuf), "pdmrg_ipc_alloc")
-            self._own.append(ptr)
-            handles.append(hbuf.raw)
+        zb, yb = int(lib.pdmrg_comm_z_bytes(self.plan._plan, world)), int(lib.pdmrg_comm_y_bytes(self.plan._plan))
+        self._own_comm = comm is None or not comm.fits(zb, yb)
+        self.peer = PeerComm(zb, yb, rank, world, dist) if self._own_comm else comm
+        self._comm = self.peer.handle
         mask = ctypes.c_uint(0)
         check(lib.pdmrg_heff_needed_j(self.plan._plan, 0, ctypes.byref(mask)), "pdmrg_heff_needed_j")
-        mine = (handles, int(mask.value))
-        if world > 1:
+        if world > 1 and mode == "bond":
             everyone = [None] * world
-            dist.all_gather_object(everyone, mine)
+            dist.all_gather_object(everyone, int(mask.value))
         else:
-            everyone = [mine]
-        self._opened = []
-        tables = []
-        for k in range(3):
-            arr = (ctypes.c_void_p * world)()
-            for q in range(world):
-                if q == rank:
-                    arr[q] = self._own[k].value
-                else:
-                    ptr = ctypes.c_void_p(0)
-                    check(lib.pdmrg_ipc_open(everyone[q][0][k], ctypes.byref(ptr)), "pdmrg_ipc_open")
-                    self._opened.append(ptr)
-                    arr[q] = ptr.value
-            tables.append(arr)
-        self._jmask = (ctypes.c_uint * world)(*[everyone[q][1] for q in range(world)])
-        self._comm = ctypes.c_void_p(0)
-        check(lib.pdmrg_comm_create(ctypes.byref(self._comm), rank, world, tables[0], tables[1], tables[2]), "pdmrg_comm_create")
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+            everyone = [int(mask.value)] * world
+        self._jmask = (ctypes.c_uint * world)(*everyone)
 
     def apply(self, x, y, sign=-1.0):
         from . import device as D
@@ -446,16 +518,12 @@ class FusedShardedHeff:
         return y
 
     def close(self):
-        import torch
-        if getattr(self, "_comm", None):
-            torch.cuda.synchronize()
-            self._lib.pdmrg_comm_destroy(self._comm)
-            self._comm = None
-            for p in self._opened:
-                self._lib.pdmrg_ipc_close(p)
-            for p in self._own:
-                self._lib.pdmrg_ipc_free(p)
-            self._opened, self._own = [], []
+        if getattr(self, "_own_comm", False) and getattr(self, "peer", None) is not None:
+            self.peer.close()
+        self.peer = None
+        self._comm = None
+        if getattr(self, "plan", None) is not None:
+            self.plan.close()
 
     def __del__(self):
         try:

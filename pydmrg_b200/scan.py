@@ -17,7 +17,7 @@ from . import mpo as mpo_lib
 from .parallel import WorkQueue, gather_scan, gather_scan_dynamic, scan_indices
 
 
-def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=6, minIter=0,
+def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol=1e-8, maxIter=10, minIter=0,
              twoSite=True, dtype="c128", continuation=False, ramp_res_tol=1e-5, stats=None, schedule="static", order=None,
              workers=1, seed=None, **solver):
     """Run ``run_dmrg(mpo_of(v), mbd=...)`` for every v in ``values`` (this rank's block only).
@@ -52,6 +52,8 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     n = len(values)
     interleave = not continuation          # cold starts: every world-th point (balanced); continuation: blocks
     workers = max(1, int(workers))
+    solver = dict(solver)
+    user_ctx = solver.pop("ctx", None)                           # one worker: the caller's context; several: one per worker
     if schedule not in ("static", "dynamic"):
         raise ValueError("schedule must be 'static' or 'dynamic'")
     dynamic = (schedule == "dynamic" or workers > 1) and not continuation
@@ -86,6 +88,11 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
                     opts = dict(solver)
                     if not last and ramp_res_tol is not None:
                         opts["res_tol"] = ramp_res_tol
+                    if not last:
+                        # the stagnation stop is for the final stage only: cutting local solves short in the cold ramp
+                        # sent 3 of 64 points of configs[3] to a metastable state (E off by 3-10 %), while the ramp's
+                        # cycles are the cheap, latency-bound ones anyway
+                        opts.pop("stagnation", None)
                     out = run_dmrg(mpo, mbd=chi, tol=tol, maxIter=maxIter if last else 0, minIter=minIter,
                                    initGuess=guess, twoSite=twoSite, dtype=dtype, returnState=True, stats=st, ctx=ctx, **opts)
                     # one-site runs leave the centre at gaugeSiteSave = N//2+1 (dmrg.py:322), two-site ones at site 0
@@ -98,7 +105,7 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
             prev = out[-1] if twoSite else (out[-1], len(mpo[0]) // 2 + 1)
 
     if workers == 1:
-        solve_points(todo, None, stats)
+        solve_points(todo, user_ctx, stats)
     else:
         import torch
         from .core import Context
@@ -138,6 +145,21 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
             "sec": secs, "points": mine}
 
 
+def scgf_shape_ok(s_vals, E, slack=1e-6):
+    """Self-check of an s-scan: the leading eigenvalue of the tilted generator is a scaled cumulant generating function,
+    hence monotone and convex in s.  A point whose sweeps got stuck in a metastable state shows up as a kink (seen with a
+    sweep cap of 4: 3 of 64 points of configs[3] were off by 3-10 %); False then."""
+    s = np.asarray(s_vals, dtype=float)
+    e = np.real(np.asarray(E))
+    o = np.argsort(s)
+    s, e = s[o], e[o]
+    if len(s) < 3:
+        return True
+    d1 = np.diff(e) / np.diff(s)
+    mono = np.all(np.diff(e) <= slack) or np.all(np.diff(e) >= -slack)
+    return bool(mono and np.all(np.diff(d1) >= -1e-3 * (1.0 + np.abs(d1[:-1]))))
+
+
 def _grow(mpsList, chi):
     from . import mps as mps_tools
     return mps_tools.increase_all_mbd([[np.array(t) for t in M] for M in mpsList], chi)
@@ -153,7 +175,7 @@ def main():
     ap.add_argument("--points", type=int, default=64)
     ap.add_argument("--smin", type=float, default=-0.5)
     ap.add_argument("--smax", type=float, default=0.5)
-    ap.add_argument("--max-iter", type=int, default=4)
+    ap.add_argument("--max-iter", type=int, default=10, help="sweep cap at the target chi (dmrg.py:309 default 10); tol ends a point earlier")
     ap.add_argument("--pin-cores", action="store_true",
                     help="give every local rank its own slice of the host cores (the scan is host-latency bound)")
     ap.add_argument("--precond", default=None, choices=[None, "diag"], help="Davidson preconditioner (default: the reference's identity)")
@@ -215,7 +237,9 @@ def main():
                           "points": args.points, "N": args.N, "chi": args.chi, "wall_sec": dt, "per_rank": per_rank,
                           "precond": args.precond, "max_space": args.max_space, "schedule": args.schedule, "workers": args.workers,
                           "restart_keep": args.restart_keep, "stagnation": args.stagnation, "blas_threads_per_rank": blas_threads,
-                          "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag]}))
+                          "E_first": [res["E"][0].real, res["E"][0].imag], "E_last": [res["E"][-1].real, res["E"][-1].imag],
+                          "E_real": [round(float(np.real(e)), 9) for e in res["E"]],
+                          "E_monotone_and_convex_in_s": scgf_shape_ok(s_vals, res["E"])}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -44,48 +44,62 @@ def main():
         mpo = M.asep_mpo(N, (0.5, 0.5, 0.1, 0.9, 0.5, 0.5, -0.5)) if model == "asep" else M.heisenberg_mpo(N)
         res = {}
         for mode in (None, "ket", "bond"):
-            spec = None if mode is None else parallel.ShardSpec(rank, world, dist, mode=mode, min_dim=32)
+            # the CPU dry run has no peer memory: NCCL-style path only; on GPUs "ket" runs the fused C++ solve, "bond" the
+            # Python loop with one all-reduce per mat-vec
+            spec = None if mode is None else parallel.ShardSpec(rank, world, dist, mode=mode, min_dim=32, fused=not emulate)
             np.random.seed(2)                                   # identical start on every rank
             st = {}
             out = dmrg.run_dmrg(mpo, mbd=chi, tol=0.0, maxIter=3, twoSite=True, dtype=dtype, stats=st, res_tol=1e-11,
                                 returnEntSpec=True, shard=spec)
             res[mode] = (complex(out[0]), float(np.real(out[1])), st.get("n_sharded_solves", 0), st.get("n_matvec", 0),
-                         st.get("n_sharded_env", 0))
+                         st.get("n_sharded_env", 0), st.get("n_fused_sharded_solves", 0))
         E0, EE0 = res[None][0], res[None][1]
         for mode in ("ket", "bond"):
-            E, EE, ns, nmv, nenv = res[mode]
+            E, EE, ns, nmv, nenv, nfused = res[mode]
             # every rank must hold the same numbers as rank 0
             t = torch.tensor([E.real, E.imag, EE], dtype=torch.float64, device=dev)
             t0 = t.clone(); dist.broadcast(t0, 0)
             same = bool(torch.equal(t, t0))
             good = abs(E - E0) < 1e-10 * abs(E0) and abs(EE - EE0) < 1e-8 and ns > 0 and nenv > 0 and same
             ok = ok and good
-            report["%s_%s" % (model, mode)] = {"dE": abs(E - E0), "dEE": abs(EE - EE0), "sharded_solves": ns, "sharded_block_updates": nenv,
+            report["%s_%s" % (model, mode)] = {"dE": abs(E - E0), "dEE": abs(EE - EE0), "sharded_solves": ns, "fused_cpp_solves": nfused, "sharded_block_updates": nenv,
                                                "n_matvec": nmv, "n_matvec_unsharded": res[None][3], "same_on_all_ranks": same}
     if os.environ.get("PDMRG_CHECK_TIMING") == "1":
-        # device-resident state as in bench.py full_sweep: ramp, then sweeps at chi; the last one is a converged sweep
+        # BASELINE configs[2] at the sweep level: entangled TASEP (s = +0.5) N=100; the state is grown ONCE through the
+        # chi ramp (unsharded, identical on every rank: same seed), then swept at chi = big unsharded and sharded from
+        # the same start -- sweep times, mat-vec counts, E and EE side by side
         from pydmrg_b200 import core, env as env_tools
         ctx = core.Context("c128")
         big = int(os.environ.get("PDMRG_CHECK_BIG_CHI", "1024"))
-        mpo = M.asep_mpo(100, (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, -0.5))
+        nsweeps = int(os.environ.get("PDMRG_CHECK_SWEEPS", "4"))
+        mpo = M.asep_mpo(100, (0.35, 0.0, 1.0, 0.0, 2.0 / 3.0, 0.0, 0.5))
+        np.random.seed(0)
+        guess = None
+        for c, rt, mi in [(c, rt, mi) for c, rt, mi in ((16, 1e-5, 0), (64, 1e-6, 0), (256, None, 1)) if c < big]:
+            out = dmrg.run_dmrg(mpo, mbd=c, tol=1e-9, maxIter=mi, twoSite=True, ctx=ctx, returnState=True, initGuess=guess, res_tol=rt)
+            guess = out[-1]
+        start = guess[0]
         for mode in (None, "ket"):
             spec = None if mode is None else parallel.ShardSpec(rank, world, dist, mode=mode)
-            np.random.seed(0)
-            out = dmrg.run_dmrg(mpo, mbd=[c for c in (16, 64, 256) if c < big], tol=1e-9, maxIter=1, twoSite=True, ctx=ctx,
-                                returnState=True)
-            mpsL = [[ctx.dev(t) for t in out[-1][0]]]
+            mpsL = [[ctx.dev(t) for t in start]]
             F = env_tools.calc_env(mpsL[0], mpo, big, gaugeSite=0, ctx=ctx)
-            cache, ts, st = {}, [], {}
-            for _ in range(5):
+            cache, ts, mv, st = {}, [], [], {}
+            for _ in range(nsweeps):
                 st = {}
                 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
                 E, mpsL, F, EE, EEs, S = dmrg.twoSiteSweep(mpsL, mpo, F, big, ctx=ctx, stats=st, recycle=cache, shard=spec)
                 torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-            report["sweep_sec_%s" % (mode or "unsharded")] = {"sec": ts, "n_matvec": st.get("n_matvec"), "E": [E.real, E.imag],
+                mv.append(st.get("n_matvec"))
+            report["sweep_sec_%s" % (mode or "unsharded")] = {"sec": [round(t, 3) for t in ts], "n_matvec": mv, "E": [E.real, E.imag], "EE": float(EE),
                                                              "sharded_solves": st.get("n_sharded_solves", 0),
+                                                             "fused_cpp_solves": st.get("n_fused_sharded_solves", 0),
                                                              "sharded_block_updates": st.get("n_sharded_env", 0)}
             del mpsL, F, cache
             torch.cuda.empty_cache()
+        a, b = report["sweep_sec_unsharded"], report["sweep_sec_ket"]
+        report["sweep_dE"] = abs(complex(*a["E"]) - complex(*b["E"]))
+        report["sweep_dEE"] = abs(a["EE"] - b["EE"])
+        ok = ok and report["sweep_dE"] < 1e-10 * abs(complex(*a["E"])) and report["sweep_dEE"] < 1e-8 and b["sharded_solves"] > 0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
