@@ -62,7 +62,7 @@ mix_kernel(MixOpDev op, const double* __restrict__ in, double* __restrict__ out,
   }
 }
 
-// The same operator with one output row per blockIdx.y: for small point spaces (chi <= 512) the kernel above has only
+// The same operator with one output row per blockIdx.y: for small point spaces (chi <= 256) the kernel above has only
 // nx*ny threads, each walking all rows through dependent metadata loads (latency bound: 15 us for 3 us of traffic at
 // chi = 256); here rows x points threads run, the row's metadata is uniform per block, and the re-reads of `in` by the
 // rows that share an input slab hit L2 (the whole intermediate is L2-resident at these sizes).
@@ -168,7 +168,7 @@ int launch_mix(int dtype, const MixOpDev& op, const void* in, void* out, int nx,
   const long long total = (long long)nx * ny;
   if (total == 0 || op.rows == 0) return 0;
   const int grid = grid_for(total, 256);
-  if (total <= 512ll * 512ll && op.rows > 1 && op.rows <= 65535) {
+  if (total <= 256ll * 256ll && op.rows > 1 && op.rows <= 65535) {     // measured: 15.5 -> 10.6 us at chi=256, but 19 -> 30 us at chi=512 (f64)
     const dim3 g2(grid, op.rows);
     if (dtype == PDMRG_C128)
       mix_rows_kernel<true><<<g2, 256, 0, stream>>>(op, (const double*)in, (double*)out, nx, ny, six, siy, sox, soy);

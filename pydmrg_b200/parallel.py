@@ -341,8 +341,8 @@ class ShardSpec:
         """This rank's ket-split shard of the local operator bound to the sweep's cached peer communicator, or None when
         the fused path does not apply (several MPO terms)."""
         from .eigs import _site_ops
-        if not getattr(self, "fused", False) or len(W) != 1:
-            return None
+        if not getattr(self, "fused", False) or len(W) != 1 or getattr(getattr(ctx, "device", None), "type", "cuda") != "cuda":
+            return None                                          # several MPO terms, or the CPU dry run of the host logic
         ops, P, shape = _site_ops(M, W, F, site, oneSite, ctx)
         fz = FusedShardedHeff(ctx.code, P, shape[-2], shape[-1], ops, ctx.ws, self.rank, self.world, self.dist, mode="ket",
                               comm=self._peer)
