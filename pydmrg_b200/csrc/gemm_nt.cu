@@ -109,10 +109,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Work items of one CTA: (tile, [k0, k1)) in processing order.  Data-parallel mode: whole tiles, strided over the grid.
 // Stream-K mode: CTA c owns the contiguous range r = gridDim.x-1-c of the global iteration space (reversed, so that the
 // finisher of a split tile only ever waits for CTAs with a LOWER index, which the hardware dispatches first).
+template <bool SK>
 struct WorkIter {
-  int mode, total_tiles, ktot, tile, step;
+  static constexpr bool mode = SK;
+  int total_tiles, ktot, tile, step;
   long long it, it_end;
-  __device__ WorkIter(const GemmParams& p, int total_tiles_, int ktot_) : mode(p.streamk), total_tiles(total_tiles_), ktot(ktot_) {
+  __device__ WorkIter(const GemmParams& p, int total_tiles_, int ktot_) : total_tiles(total_tiles_), ktot(ktot_) {
     if (mode) {
       const long long total = (long long)total_tiles * ktot;
       const long long r = (long long)gridDim.x - 1 - blockIdx.x;
@@ -140,7 +142,7 @@ struct WorkIter {
   }
 };
 
-template <bool CPLX, int MI, bool SCATTER = false>
+template <bool CPLX, int MI, bool SCATTER = false, bool SK = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -176,7 +178,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const int ktot_p = p.kiters * nb2_k;
-      WorkIter wi(p, total_tiles, ktot_p);
+      WorkIter<SK> wi(p, total_tiles, ktot_p);
       int tile, k0, k1;
       while (wi.next(tile, k0, k1)) {
         const int tm = tile % p.tiles_m;
@@ -186,8 +188,9 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rowA = tm * BM, rowB = tn * B_ROWS;
         const int b1 = b / nb2_out;
         const int a1 = p.bcastA1 ? 0 : b1, c1 = p.bcastB1 ? 0 : b1;
-        for (int kglob = k0; kglob < k1; ++kglob) {
-          const int q = kglob / p.kiters, kit = kglob - q * p.kiters;
+        int q = SK ? k0 / p.kiters : 0, kit = SK ? k0 - q * p.kiters : 0;       // data-parallel segments start at k = 0
+        for (int kglob = k0; kglob < k1; ++kglob, ++kit) {
+          if (kit == p.kiters) { kit = 0; ++q; }
           const int b2 = p.idx2[p.accum2 ? q : b % p.nb2];
           const int a2 = p.bcastA2 ? 0 : b2, c2 = p.bcastB2 ? 0 : b2;
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -225,7 +228,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   int stage = 0;
   uint32_t phase = 0;
   const int ktot = p.kiters * nb2_k;
-  WorkIter wi(p, total_tiles, ktot);
+  WorkIter<SK> wi(p, total_tiles, ktot);
   int tile, seg_k0, seg_k1;
   while (wi.next(tile, seg_k0, seg_k1)) {
     const int tm = tile % p.tiles_m;
@@ -274,7 +277,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
 
-    if (!SCATTER && p.streamk && !(seg_k0 == 0 && seg_k1 == ktot)) {
+    if (SK && !(seg_k0 == 0 && seg_k1 == ktot)) {
       constexpr int FRAG = MI * 8;                               // accumulator doubles per thread
       const int ctid = threadIdx.x;                              // consumer thread id, 0..255
       if (seg_k0 != 0) {
@@ -677,6 +680,15 @@ static int gemm_nt_impl(int dtype, int M, int N, int K, int nb1, int nb2, const 
         if (cplx) gemm_nt_dmma_kernel<true, 4, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
         else gemm_nt_dmma_kernel<false, 4, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
       }
+    } else if (p.streamk) {
+      static bool attr3 = false;
+      if (!attr3) {
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<true, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PDMRG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel<false, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr3 = true;
+      }
+      if (cplx) gemm_nt_dmma_kernel<true, 8, false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+      else gemm_nt_dmma_kernel<false, 8, false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
     } else if (bm == 128) {
       if (cplx) gemm_nt_dmma_kernel<true, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
       else gemm_nt_dmma_kernel<false, 8><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);

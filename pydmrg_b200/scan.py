@@ -72,7 +72,7 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
         from . import mps as mps_tools
         with seed_lock:
             np.random.seed(int(seed) + int(idx))
-            return mps_tools.make_all_mps_right(mps_tools.create_all_mps(len(mpo_of(values[idx])[0]), chi, 1))
+            return mps_tools.make_all_mps_right(mps_tools.create_all_mps(len(mpo_of(values[idx])[0]), chi, int(solver.get("nStates", 1))))
 
     def solve_points(points, ctx, st):
         prev = None
@@ -182,8 +182,9 @@ def main():
     ap.add_argument("--max-space", type=int, default=12, help="Davidson subspace before a restart (reference: 12)")
     ap.add_argument("--workers", type=int, default=3, help="concurrent scan points per GPU (host threads, one CUDA stream each)")
     ap.add_argument("--restart-keep", type=int, default=0, help="thick restart of the Davidson subspace (0: the reference's restart)")
-    ap.add_argument("--stagnation", type=int, default=30, help="stop a local solve whose residual was not halved within this many cycles "
-                                                               "(0: the reference's behaviour, up to 1000 cycles per solve)")
+    ap.add_argument("--stagnation", type=int, default=0, help="final chi stage: stop a local solve whose residual was not halved within this "
+                                                              "many cycles (0 = the reference's behaviour, up to 1000 cycles per solve; 30 makes the "
+                                                              "two points next to s=0 12x cheaper but sent 1 of 8 test points to a complex branch)")
     ap.add_argument("--schedule", default="dynamic", choices=["static", "dynamic"],
                     help="dynamic: a rank takes the next point when it is free, points nearest s = 0 (the expensive ones) first")
     args = ap.parse_args()
