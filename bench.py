@@ -259,7 +259,11 @@ def main():
         run_reference(args, rank, world)
         return
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 must print ONE JSON line on stdout, but NCCL writes its version banner there from C (whatever NCCL_DEBUG says
+    # on this image): everything that goes to fd 1 during the run is sent to stderr, the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -475,10 +479,12 @@ def main():
         if npts:
             extra("scan", lambda: scan_multi(npts, 0, 1, None), need=45.0)
         line["extras_sec"] = time.perf_counter() - t_start
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    os.close(real_stdout)
 
 
 def bond_step(args, ctx, plan, L, R, W1, W2, chi):
@@ -709,7 +715,7 @@ def scan_multi(points, rank, world, dist, max_iter=10):
         dist.barrier()
     t0 = time.perf_counter()
     res = scan.run_scan(mpo_of, s_vals, 256, rank, world, dist if world > 1 else None, maxIter=max_iter, tol=1e-8, schedule="dynamic",
-                        order=order, workers=3, seed=0, stats=st)
+                        order=order, workers=3, seed=[pool.index(i) for i in idx], stats=st)     # one seed per GRID point, whatever the subset
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

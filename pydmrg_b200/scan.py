@@ -43,7 +43,8 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     in the chi ramp and at the chain ends: a Davidson cycle is ~12 tiny kernels and a host round trip), so one point
     leaves the GPU idle most of the time; concurrent points fill it.  The C-ABI calls release the GIL, the library keeps
     its cuSOLVER / cuBLAS handles, pinned staging and stream-K scratch per thread / per stream.
-    ``seed``: the random start of point i is drawn from np.random.seed(seed + i) (reproducible whatever the schedule);
+    ``seed``: the random start of point i is drawn from np.random.seed(seed + i), or seed[i] when a sequence is given
+    (reproducible whatever the schedule);
     default: the global NumPy state as the reference uses it (only reproducible with one worker and a static schedule).
 
     Returns dict(E, EE: full-length complex arrays (gathered), sec: per-point wall seconds of this
@@ -71,7 +72,7 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
             return None
         from . import mps as mps_tools
         with seed_lock:
-            np.random.seed(int(seed) + int(idx))
+            np.random.seed(int(seed[idx]) if np.ndim(seed) else int(seed) + int(idx))
             return mps_tools.make_all_mps_right(mps_tools.create_all_mps(len(mpo_of(values[idx])[0]), chi, int(solver.get("nStates", 1))))
 
     def solve_points(points, ctx, st):
