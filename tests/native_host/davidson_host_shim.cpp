@@ -12,6 +12,7 @@
 
 typedef std::complex<double> cd;
 struct pdmrg_heff_plan;
+struct pdmrg_comm;
 typedef int (*matvec_cb)(const double* x, double* y, double sign);
 
 namespace pdmrg {
@@ -41,6 +42,13 @@ const char* cudaGetErrorString(int) { return "host shim"; }
 // ---- mat-vec ----------------------------------------------------------------------------------------------------
 int pdmrg_heff_apply(pdmrg_heff_plan*, const void* const*, const void* const*, const void* x, void* y, double sign, void*,
                      size_t, void*) {
+  ++g_launches;
+  return g_cb((const double*)x, (double*)y, sign);
+}
+
+// the sharded loop's mat-vec (pdmrg_davidson_sharded): one "rank" on the host = the same callback
+int pdmrg_heff_apply_fused_ket(pdmrg_heff_plan*, pdmrg_comm*, const void* const*, const void* const*, const void* x, void* y,
+                               double sign, void*, size_t, void*) {
   ++g_launches;
   return g_cb((const double*)x, (double*)y, sign);
 }

@@ -37,13 +37,13 @@ def host_lib(tmp_path_factory):
     return lib
 
 
-def run_native(lib, A, x0s, code, nroots=1, max_space=12, res_tol=None, lindep=1e-14, diag=None, floor=0.1, max_cycle=1000):
+def run_native(lib, A, x0s, code, nroots=1, max_space=12, res_tol=None, lindep=1e-14, diag=None, floor=0.1, max_cycle=1000, ex=None):
     """Drive pdmrg_davidson[_precond] exactly as pydmrg_b200/davidson.py:davidson_native does, on NumPy buffers."""
     n = A.shape[0]
     dt = np.complex128 if code == 1 else np.float64
     E = 2 if code == 1 else 1
     ms = max_space + 3 * nroots
-    rows = ms + nroots
+    rows = ms + nroots + (int(ex.get("restart_keep", 0)) if ex else 0)
     XS = np.zeros((rows, n), dt); AX = np.zeros((rows, n), dt); R = np.zeros((2 * nroots + 2, n), dt)
     for k, g in enumerate(x0s):
         R[nroots + k] = g
@@ -68,7 +68,13 @@ def run_native(lib, A, x0s, code, nroots=1, max_space=12, res_tol=None, lindep=1
             max_space, ctypes.c_double(lindep), ctypes.c_double(-1.0 if res_tol is None else res_tol), max_cycle, 0, P(XS), P(AX), P(R),
             ctypes.c_longlong(n), None, ctypes.c_size_t(0), P(scratch), ctypes.c_size_t(scratch.size), e_host, P(out),
             ctypes.c_longlong(n), ctypes.byref(n_mv), ctypes.byref(cyc), ctypes.byref(last), None]
-    if diag is None:
+    if ex is not None:
+        d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+        n_rs = ctypes.c_int(0)
+        rc = lib.pdmrg_davidson_ex(*args, None if d is None else P(d), ctypes.c_double(floor), int(ex.get("restart_keep", 0)),
+                                   int(ex.get("tol_relative", 0)), ctypes.byref(n_rs), int(ex.get("stagnation", 0)))
+        ex["n_restarts"] = n_rs.value
+    elif diag is None:
         rc = lib.pdmrg_davidson(*args)
     else:
         d = np.ascontiguousarray(diag, dtype=dt)
@@ -153,3 +159,57 @@ def test_native_loop_with_the_diagonal_preconditioner(host_lib, golden):
     a = run_native(host_lib, S, [x], 0, res_tol=1e-10)
     b = run_native(host_lib, S, [x], 0, res_tol=1e-10, diag=np.diag(S), floor=0.1)
     assert abs(a[0][0] - b[0][0]) < 1e-9 and abs(b[0][0].real - np.linalg.eigvalsh(S)[0]) < 1e-9 and b[4] <= 1e-10
+
+
+def test_native_thick_restart_relative_tolerance_and_stagnation(host_lib, golden):
+    """pdmrg_davidson_ex on the host: thick restarts reach the same eigenpair as the reference's restart with fewer
+    mat-vecs on a problem that needs many restarts; ARPACK's relative stopping rule stops earlier; the stagnation stop
+    ends a solve that cannot make progress (a defective 2x2 block at the bottom of the spectrum) long before max_cycle."""
+    g = golden["davidson"]
+    L, R, W, x0 = g["L"], g["R"], g["W"], g["x0"]
+    A = -orc.heff_dense_onesite([L], [W], [R], x0.shape)
+    base = run_native(host_lib, A, [x0.ravel()], 1, res_tol=1e-10, max_cycle=5000)
+    ex = {"restart_keep": 4}
+    thick = run_native(host_lib, A, [x0.ravel()], 1, res_tol=1e-10, max_cycle=5000, ex=ex)
+    assert abs(thick[0][0] - base[0][0]) < 1e-9 * abs(base[0][0]) and thick[4] <= 1e-10
+    assert ex["n_restarts"] > 0 and thick[2] < base[2]
+    assert np.linalg.norm(A @ thick[1][0] - thick[0][0] * thick[1][0]) < 2e-10
+    # two roots, real dtype
+    rng = np.random.default_rng(7)
+    B = rng.standard_normal((300, 300)) * 0.02
+    S = (B + B.T) / 2 + np.diag(np.linspace(0, 1, 300) ** 3)                # clustered bottom of the spectrum
+    xs = [rng.standard_normal(300), rng.standard_normal(300)]
+    ex2 = {"restart_keep": 6}
+    e2, v2, nmv2, _, last2 = run_native(host_lib, S, xs, 0, nroots=2, res_tol=1e-9, max_cycle=4000, ex=ex2)
+    ref = np.linalg.eigvalsh(S)[:2]
+    assert np.max(np.abs(np.sort(e2.real) - ref)) < 1e-8 and ex2["n_restarts"] > 0
+    # ARPACK's rule ||r|| <= tol |theta|
+    rel = run_native(host_lib, A, [x0.ravel()], 1, res_tol=1e-5, max_cycle=5000, ex={"restart_keep": 4, "tol_relative": 1})
+    assert rel[2] < thick[2] and rel[4] <= 1e-5 * abs(rel[0][0]) * 1.0001
+    # a Jordan-like block at the bottom: residual stalls; the stagnation stop gives up early, the plain loop does not
+    n = 80
+    J = np.diag(np.linspace(1.0, 5.0, n)).astype(np.complex128)
+    J[0, 0] = J[1, 1] = -1.0
+    J[0, 1] = 1.0                                                           # defective pair at -1
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    Jd = Q @ J @ Q.conj().T
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    plain = run_native(host_lib, Jd, [x], 1, res_tol=1e-13, max_cycle=400)
+    stag = run_native(host_lib, Jd, [x], 1, res_tol=1e-13, max_cycle=400, ex={"stagnation": 20})
+    assert stag[3] < plain[3] and abs(stag[0][0] + 1.0) < 1e-4
+
+
+def test_native_tie_break_on_a_complex_conjugate_pair(host_lib):
+    """Lowest real part shared by a complex-conjugate pair: the loop settles on ONE member and converges (which one is
+    decided while the two Ritz values still differ in their real parts), instead of flipping between the two from
+    cycle to cycle once their real parts agree to rounding."""
+    rng = np.random.default_rng(11)
+    n = 60
+    D = np.diag(np.linspace(0.5, 6.0, n)).astype(np.complex128)
+    D[0, 0], D[1, 1] = -1.0 + 0.3j, -1.0 - 0.3j
+    X = np.eye(n) + 0.05 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    A = X @ D @ np.linalg.inv(X)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    e, v, nmv, cyc, last = run_native(host_lib, A, [x], 1, res_tol=1e-10, max_cycle=600)
+    assert min(abs(e[0] - (-1.0 + 0.3j)), abs(e[0] - (-1.0 - 0.3j))) < 1e-8 and last <= 1e-10 and cyc < 300
+    assert np.linalg.norm(A @ v[0] - e[0] * v[0]) < 1e-9 * np.linalg.norm(v[0])

@@ -213,3 +213,21 @@ def test_two_site_two_state_sweeps_host_flow(T, monkeypatch):
     assert abs(E[0] - Eo[0]) < 1e-9 and abs(E[1] - Eo[1]) < 1e-9 and abs(EE - EEo) < 1e-7
     for site in range(1, N):                                   # isometries are shared, the centre (site 0) is not
         assert mpsL[0][site] is mpsL[1][site] or torch.equal(mpsL[0][site], mpsL[1][site])
+
+
+def test_recycled_weight_check_and_rdm_spectrum_length():
+    """(a) a warm-started step whose discarded weight exceeds twice that of the bond's last exact decomposition
+    is rejected (the caller redoes the bond exactly); (b) the one-site RDM spectrum has min(d*Dl, Dr) entries, like the
+    reference's calc_ent_right / calc_ent_left (dmrg.py:30-47), not d*Dl."""
+    from pydmrg_b200 import truncate as T
+    cache = {}
+    T.note_exact_visit(cache, 5, (64, 64, 32), 1e-9)
+    assert T.recycled_weight_ok(cache, 5, 1.5e-9) and not T.recycled_weight_ok(cache, 5, 3e-9)
+    assert T.recycled_weight_ok(cache, 6, 1.0)                              # no exact visit on record: nothing to compare with
+    T.note_exact_visit(cache, 7, (64, 64, 32), 0.0)
+    assert T.recycled_weight_ok(cache, 7, 5e-14) and not T.recycled_weight_ok(cache, 7, 1e-12)
+    w = np.sort(np.concatenate([np.zeros(12), np.array([0.5, 0.3, 0.15, 0.05])]))     # ascending, as heevd returns them
+    EE, spec, S = T._spectrum_from_rdm(w, 4)
+    assert len(spec) == 4 and len(S) == 4 and abs(np.sum(S ** 2) - 1) < 1e-14
+    p = np.array([0.5, 0.3, 0.15, 0.05])
+    assert abs(EE - np.sum(-p * np.log2(p))) < 1e-14
