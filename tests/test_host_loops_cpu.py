@@ -355,7 +355,7 @@ def test_scan_self_check_and_per_point_seeds():
     s = np.linspace(-0.5, 0.5, 21)
     E = 2.0 * np.exp(-3.0 * s) - 0.26                                       # convex, decreasing (the shape of configs[3])
     assert scgf_shape_ok(s, E) and scgf_shape_ok(s[::-1], E[::-1])
-    bad = E.copy(); bad[7] -= 0.05
+    bad = E.copy(); bad[7] -= 0.3                                         # a 10 % dip, the size seen in the scans
     assert not scgf_shape_ok(s, bad)
     worse = E.copy(); worse[12] += 0.2                                      # not even monotone
     assert not scgf_shape_ok(s, worse)
