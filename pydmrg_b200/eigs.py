@@ -179,10 +179,11 @@ def calc_eigs(mpsL, W, F, site, nStates, alg="davidson", preserveState=False, ed
         # fixed-order reductions = identical control flow on all ranks, with no collective inside the solve
         for gk in guesses:
             shard.consensus(gk)
-        pcf = dict(diag=fused.plan.diag(-1.0), precond_floor=precond_floor) if precond == "diag" else {}
+        # (the preconditioner ``pc`` holds the diagonal of the WHOLE operator from the unsharded plan, identical on every
+        # rank -- the shard's own diagonal covers its ket range only and would make the ranks diverge)
         vals, vecs = davidson(None, guesses, n, ctx.code, ctx.device, nroots=nS, lindep=lindep, res_tol=res_tol,
                               fixed_cycles=fixed_cycles, stats=stats, plan=fused.plan, native=True, max_cycle=max_cycle,
-                              max_space=max_space, restart_keep=restart_keep, stagnation=stagnation, comm=fused._comm, **pcf)
+                              max_space=max_space, restart_keep=restart_keep, stagnation=stagnation, comm=fused._comm, **pc)
         fused.peer.check()
         E = -vals
         fused.close()

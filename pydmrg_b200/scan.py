@@ -52,7 +52,7 @@ def run_scan(mpo_of, values, mbd, rank=0, world=1, dist=None, ramp=(16, 64), tol
     from .dmrg import run_dmrg
     n = len(values)
     interleave = not continuation          # cold starts: every world-th point (balanced); continuation: blocks
-    workers = max(1, int(workers))
+    workers = 1 if continuation else max(1, int(workers))      # a continuation is serial by definition
     solver = dict(solver)
     user_ctx = solver.pop("ctx", None)                           # one worker: the caller's context; several: one per worker
     if schedule not in ("static", "dynamic"):
